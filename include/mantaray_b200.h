@@ -1,0 +1,262 @@
+/*
+ * mantaray_b200.h — C ABI of the B200-native batch ray tracer.
+ *
+ * This is the drop-in boundary for ONE path of mines-oceanography/mantaray:
+ * the per-ray RK4 integration of the wave ray equations over gridded
+ * bathymetry and surface currents.  Citations are file:line into the
+ * reference tree.
+ *
+ *   reference                                   replaced by
+ *   ------------------------------------------  ---------------------------
+ *   ffi::ray_tracing        src/ffi.rs:51-85     mr_fields_open_netcdf3 + mr_trace_many
+ *   ffi::single_ray         src/ffi.rs:25-49     mr_fields_open_netcdf3 + mr_single_ray
+ *   ManyRays::trace_many    src/ray.rs:98-127    mr_trace_many
+ *   SingleRay::trace_individual src/ray.rs:198-213  mr_single_ray
+ *   CartesianNetcdf3::open  src/bathymetry/cartesian_netcdf3.rs:167-256   mr_fields_open_netcdf3
+ *   CartesianCurrent::open  src/current/cartesian_current.rs:58-213       mr_fields_open_netcdf3
+ *   trait BathymetryData    src/bathymetry/mod.rs:35-41   mr_bathymetry_desc (kind tag)
+ *   trait CurrentData       src/current/mod.rs:21-31      mr_current_desc   (kind tag)
+ *   (commented extern "C" stub  src/ffi.rs:87-107; cbindgen.toml; Cargo.toml:45-50 `capi`)
+ *
+ * The reference's live FFI is PyO3; its C ABI is a commented-out stub.  This
+ * header is what that stub would have grown into.  Plain C: pointers, sizes,
+ * POD structs; no C++/CUDA/torch types.
+ *
+ * Conventions
+ *   - every function returns an int status (MR_OK == 0, errors < 0); the text
+ *     of the last error on the calling thread is at mr_last_error().
+ *   - numerical conditions are never errors: as in the reference
+ *     (src/wave_ray_path.rs:220-234) a failing right-hand side becomes four
+ *     NaNs, the NaN row is stored and the ray stops (solout, :236-246).
+ *   - the caller owns every output buffer; the library never frees caller
+ *     memory.  Field handles are opaque and freed with mr_fields_free.
+ *   - there is NO CPU fallback.  Without a CUDA device every compute entry
+ *     point fails with MR_ERR_CUDA.
+ */
+#ifndef MANTARAY_B200_H
+#define MANTARAY_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MR_ABI_VERSION 1
+
+/* ---- status codes -------------------------------------------------------- */
+#define MR_OK            0
+#define MR_ERR_IO       -1   /* file cannot be opened / read                        */
+#define MR_ERR_BAD_ARG  -2   /* NULL pointer, bad size, bad kind, dt<=0, ...        */
+#define MR_ERR_CUDA     -3   /* no device, launch/copy failure                      */
+#define MR_ERR_OOM      -4   /* host or device allocation failed                    */
+#define MR_ERR_FORMAT   -5   /* not a NetCDF-3 file / variable missing / bad shape  */
+
+/* ---- field descriptors --------------------------------------------------- */
+
+/* Implementors of BathymetryData (src/bathymetry/mod.rs:35-41). */
+#define MR_BATHY_CONSTANT 0  /* ConstantDepth  src/bathymetry/constant_depth.rs:26-46 */
+#define MR_BATHY_SLOPE    1  /* ConstantSlope  src/bathymetry/constant_slope.rs:52-76 */
+#define MR_BATHY_GRID     2  /* CartesianNetcdf3 src/bathymetry/cartesian_netcdf3.rs:35-43 */
+#define MR_BATHY_ARRAY    3  /* ArrayDepth     src/bathymetry/array_depth.rs:9-36 (test aid) */
+
+/* Implementors of CurrentData (src/current/mod.rs:21-31). */
+#define MR_CURRENT_CONSTANT 0 /* ConstantCurrent  src/current/constant_current.rs:51-77 */
+#define MR_CURRENT_GRID     1 /* CartesianCurrent src/current/cartesian_current.rs:18-27 */
+
+/*
+ * Bathymetry.  All pointers are HOST pointers; mr_fields_create copies what it
+ * needs, so they may be released as soon as it returns.
+ *   CONSTANT: depth h0 everywhere.
+ *   SLOPE   : h = h0 + dhdx*(x-x0) + dhdy*(y-y0), evaluated in float.
+ *   GRID    : x[nx], y[ny] float coordinates (equally spaced, ascending),
+ *             depth[ny*nx] double, row-major with x fastest: depth[nx*yi+xi]
+ *             (src/bathymetry/cartesian_netcdf3.rs:465-471).  nx,ny >= 2.
+ *   ARRAY   : array[nx*ny] float, array[xi*ny + yi] is the reference's
+ *             array[xi][yi]; the reference bounds-checks BOTH indices against
+ *             the outer length nx (src/bathymetry/array_depth.rs:30), so
+ *             ny >= nx is required.
+ */
+typedef struct mr_bathymetry_desc {
+    int32_t kind;
+    int32_t nx, ny;
+    const float  *x, *y;
+    const double *depth;
+    const float  *array;
+    float h0, x0, y0, dhdx, dhdy;
+} mr_bathymetry_desc;
+
+/*
+ * Surface current.
+ *   CONSTANT: (u0, v0) everywhere, zero gradients.
+ *   GRID    : x[nx], y[ny], u[ny*nx], v[ny*nx], all double, u[nx*yi+xi]
+ *             (src/current/cartesian_current.rs:421-427).  nx,ny >= 2.
+ */
+typedef struct mr_current_desc {
+    int32_t kind;
+    int32_t nx, ny;
+    const double *x, *y, *u, *v;
+    double u0, v0;
+} mr_current_desc;
+
+/* Opaque: the two fields, resident on every device selected at creation. */
+typedef struct mr_fields mr_fields;
+
+/* ---- options -------------------------------------------------------------- */
+
+/* Arithmetic of the f64 part of the right-hand side.  The f32 part (position
+ * rounding, fractional index, bilinear interpolation) is value-identical to
+ * the reference in both modes.
+ *   MR_MATH_FAST  : restructured f64 math (one exponential per evaluation,
+ *                   direction cosines from kx/k, reciprocal-multiply), FMA on.
+ *   MR_MATH_STRICT: the reference's expression tree operation by operation
+ *                   (atan2/sin/cos, tanh/sinh/cosh, every divide), FMA off.   */
+#define MR_MATH_FAST   0
+#define MR_MATH_STRICT 1
+
+typedef struct mr_trace_opts {
+    int32_t stride;       /* store every stride-th row (row j = step j*stride); 1 = reference; 0 -> 1 */
+    int32_t math;         /* MR_MATH_FAST (default) or MR_MATH_STRICT                                 */
+    int32_t chunk_rays;   /* host path: rays per device slab (0 = automatic)                          */
+    int32_t reserved;
+} mr_trace_opts;
+
+/* ---- library ------------------------------------------------------------- */
+
+int         mr_abi_version(void);
+/* Number of usable CUDA devices (0 when there is none; never an error). */
+int         mr_device_count(void);
+/* Last error message of the calling thread ("" if none). Never NULL. */
+const char *mr_last_error(void);
+
+/* ---- fields -------------------------------------------------------------- */
+
+/* Upload both fields to every device in device_mask (bit i = CUDA device i;
+ * 0 means "device 0").  Grids are replicated per device. */
+int  mr_fields_create(const mr_bathymetry_desc *bathy, const mr_current_desc *current,
+                      uint32_t device_mask, mr_fields **out);
+
+/* What src/ffi.rs:36-38 / :62-64 does: open two NetCDF-3 files, variables
+ * "x","y","depth" and "x","y","u","v".  Same dtype handling as the reference:
+ * any of {i8,u8,i16,i32,f32,f64}; bathymetry coordinates become float, depth
+ * double; current everything double; the dimension order recorded in the file
+ * is ignored and the flat variable is indexed [y][x].  Either path may be NULL
+ * to get the reference defaults (ConstantDepth 2000 m, src/bathymetry/
+ * constant_depth.rs:9; ConstantCurrent (0,0), src/current/constant_current.rs:10). */
+int  mr_fields_open_netcdf3(const char *bathymetry_path, const char *current_path,
+                            uint32_t device_mask, mr_fields **out);
+
+void mr_fields_free(mr_fields *f);
+
+/* Devices the handle lives on, as a bit mask. */
+uint32_t mr_fields_device_mask(const mr_fields *f);
+
+/* ---- sizes --------------------------------------------------------------- */
+
+/* Number of RK4 steps the stepper takes: ceil((t_end - t0)/dt)
+ * (ode_solvers 0.4.0 Rk4::integrate; called from src/ray.rs:207-208).
+ * Returns -1 if dt is not > 0 or the quotient is not finite / negative
+ * (the reference panics on those). */
+int64_t mr_num_steps(double t0, double t_end, double dt);
+/* Rows a trajectory buffer must hold: num_steps/stride + 1. */
+int64_t mr_num_rows(double t0, double t_end, double dt, int32_t stride);
+
+/* ---- tracing: host buffers ----------------------------------------------- */
+
+/*
+ * ManyRays::trace_many (src/ray.rs:98-127) for n rays, initial states
+ * (x0[i], y0[i], kx0[i], ky0[i]).  Rays are split in contiguous blocks over
+ * the devices of the handle; there is no cross-ray communication.
+ *
+ * Outputs (all HOST memory, caller-owned, any of them may be NULL):
+ *   t [rows_cap]            time of row j: t0, then accumulated += dt*stride steps
+ *   x,y,kx,ky [rows_cap][n] step-major, ray fastest: x[j*n + i].  Rows a ray
+ *                           never reached are NaN, as mantaray.core.ray_tracing
+ *                           pads them (python/mantaray/core.py:115-119).
+ *   rows [n]                rows the reference would have stored for ray i
+ *                           (1 + executed steps, including the trailing all-NaN
+ *                           row that stops the ray), counted at stride 1.
+ *   len  [n]                leading rows without any NaN (the rule of
+ *                           RayResult::from, src/ray_result.rs:123-151), stride 1.
+ *   final_state [4][n]      x,y,kx,ky of the last NaN-free row.
+ * rows_cap = mr_num_rows(t0,t_end,dt,stride).
+ */
+int  mr_trace_many(mr_fields *f, int64_t n,
+                   const double *x0, const double *y0, const double *kx0, const double *ky0,
+                   double t0, double t_end, double dt, const mr_trace_opts *opts,
+                   double *t, double *x, double *y, double *kx, double *ky,
+                   int32_t *rows, int32_t *len, double *final_state);
+
+/*
+ * SingleRay::trace_individual (src/ray.rs:198-213) as ffi::single_ray returns
+ * it (src/ffi.rs:42-47): rows of (t, x, y, kx, ky), array-of-structs,
+ * out[5*j + c].  out holds out_cap rows; *n_rows receives the number of rows
+ * the ray produced (including the trailing NaN row).  If out_cap is too small
+ * the call fails with MR_ERR_BAD_ARG and *n_rows holds the required size.
+ */
+int  mr_single_ray(mr_fields *f, double x0, double y0, double kx0, double ky0,
+                   double t0, double t_end, double dt, const mr_trace_opts *opts,
+                   double *out, int64_t out_cap, int64_t *n_rows);
+
+/* ---- tracing: device-resident -------------------------------------------- */
+
+/*
+ * The same integration with every buffer already in device memory of CUDA
+ * device `device` (which must be in the handle's mask), enqueued on `stream`
+ * (a cudaStream_t passed as void*; NULL = the legacy default stream) and NOT
+ * synchronised: the call returns as soon as the work is queued.
+ *   d_x..d_ky  [rows_cap][ld] with ld >= n the row pitch in elements
+ *              (may all be NULL: "len and final state only");
+ *   d_rows, d_len [n]; d_final [4][n]  (each may be NULL).
+ * *launches, if not NULL, receives the number of kernels enqueued.
+ */
+int  mr_trace_device(mr_fields *f, int device, void *stream, int64_t n,
+                     const double *d_x0, const double *d_y0, const double *d_kx0, const double *d_ky0,
+                     double t0, double t_end, double dt, const mr_trace_opts *opts,
+                     double *d_x, double *d_y, double *d_kx, double *d_ky, int64_t ld,
+                     int32_t *d_rows, int32_t *d_len, double *d_final, int32_t *launches);
+
+/* ---- NetCDF-3 ingest -------------------------------------------------------- */
+
+/*
+ * The reader behind mr_fields_open_netcdf3, exposed so the host-side mirrors of
+ * CartesianNetcdf3::open / CartesianCurrent::open can be tested and reused.
+ * Classic (CDF-1) and 64-bit-offset (CDF-2) files, fixed and record variables.
+ * nc_type codes: 1 byte(i8) 2 char(u8) 3 short(i16) 4 int(i32) 5 float 6 double.
+ * Works without a CUDA device.
+ */
+typedef struct mr_nc3 mr_nc3;
+#define MR_NC3_MAX_DIMS 8
+int  mr_nc3_open(const char *path, mr_nc3 **out);
+void mr_nc3_close(mr_nc3 *f);
+int  mr_nc3_var_count(const mr_nc3 *f);
+/* Name of variable `index` copied into buf (NUL-terminated, truncated to cap). */
+int  mr_nc3_var_name(const mr_nc3 *f, int index, char *buf, size_t cap);
+/* Type, element count and shape of a variable; MR_ERR_FORMAT if absent. */
+int  mr_nc3_var_info(const mr_nc3 *f, const char *name, int32_t *nc_type, int64_t *n_elems,
+                     int32_t *ndims, int64_t dims[MR_NC3_MAX_DIMS]);
+/* Whole variable, flat, cast the way the reference's dtype switch casts it
+ * (`as f32` / `as f64`).  cap = capacity of out in elements. */
+int  mr_nc3_read_f32(const mr_nc3 *f, const char *name, float *out, int64_t cap);
+int  mr_nc3_read_f64(const mr_nc3 *f, const char *name, double *out, int64_t cap);
+
+/* ---- pinned host memory ---------------------------------------------------- */
+
+/* Page-locked host allocations for trajectory buffers, so the device-to-host
+ * gather of mr_trace_many runs at full PCIe rate and overlaps the kernels. */
+int  mr_host_alloc(size_t bytes, void **out);
+void mr_host_free(void *p);
+
+/* ---- measurement aids ----------------------------------------------------- */
+
+/* Sustained FP64 FMA throughput of `device` in TFLOP/s (2 flop per DFMA),
+ * measured with a register-only DFMA kernel timed by CUDA events over
+ * `millis` ms of work.  This is the denominator of the FP64 roofline; it is
+ * measurement plumbing, not part of the path. */
+int  mr_measure_fp64_peak(int device, int millis, double *tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MANTARAY_B200_H */

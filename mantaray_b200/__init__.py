@@ -1,0 +1,22 @@
+"""mantaray_b200 — B200-native batch ray tracing behind mantaray's API.
+
+``single_ray`` and ``ray_tracing`` have the signatures of
+``mantaray.core`` (python/mantaray/core.py); the field types and the batch
+driver (``ManyRays`` / ``SingleRay``) mirror the Rust crate's.  The integration
+runs as hand-written sm_100a CUDA kernels behind the C ABI of
+``include/mantaray_b200.h``; importing the package does not load the shared
+library, calling into it does (and fails loudly when it is missing).
+"""
+
+from ._abi import MR_MATH_FAST, MR_MATH_STRICT
+from ._capi import Fields, ManyRays, MantarayError, RayState, SingleRay, TraceResult, trace_many
+from .core import ray_tracing, single_ray
+from .fields import (ArrayDepth, CartesianCurrent, CartesianNetcdf3, ConstantCurrent, ConstantDepth,
+                     ConstantSlope)
+
+__all__ = [
+    "single_ray", "ray_tracing",
+    "ManyRays", "SingleRay", "RayState", "Fields", "TraceResult", "trace_many", "MantarayError",
+    "ConstantDepth", "ConstantSlope", "CartesianNetcdf3", "ArrayDepth", "ConstantCurrent", "CartesianCurrent",
+    "MR_MATH_FAST", "MR_MATH_STRICT",
+]

@@ -1,0 +1,727 @@
+// mr_capi.cu — the C ABI of include/mantaray_b200.h.
+//
+// Host side of the batch driver: what ffi.rs (src/ffi.rs:25-85) and
+// ManyRays/SingleRay (src/ray.rs:24-214) do around the integration — open the
+// two field files, build the ray states, run, hand the rows back — with the
+// integration itself being the CUDA kernel of mr_trace_kernel.cuh.
+//
+// Multi-GPU: rays are independent (src/ray.rs:112-123 maps them independently),
+// so a handle replicates the field grids on every selected device and
+// mr_trace_many gives each device one contiguous block of rays, driven by its
+// own host thread and streams.  No collective is involved; the "gather" is each
+// device copying its column block of the step-major [rows][n] host arrays.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <memory>
+#include <mutex>
+#include <thread>
+
+#include "mr_internal.hpp"
+#include "mr_launch.hpp"
+#include "mr_trace_kernel.cuh"
+
+namespace mr {
+
+// ---- errors ---------------------------------------------------------------
+static thread_local std::string g_err;
+void set_error(const std::string &msg) { g_err = msg; }
+int fail(int code, const std::string &msg)
+{
+    g_err = msg;
+    return code;
+}
+static int cuda_fail(cudaError_t e, const char *what)
+{
+    int code = (e == cudaErrorMemoryAllocation) ? MR_ERR_OOM : MR_ERR_CUDA;
+    return fail(code, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define MR_CUDA(call)                                                 \
+    do {                                                              \
+        cudaError_t e__ = (call);                                     \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call);         \
+    } while (0)
+
+// ---- DFMA probe -------------------------------------------------------------
+__global__ void __launch_bounds__(256) dfma_probe_kernel(double *sink, int iters)
+{
+    // 8 independent chains per thread keep the FP64 pipe full at any occupancy
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3;
+    double a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 0.999999999, c = 1e-12;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+            a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+        }
+    }
+    double s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (s == 123.456) sink[0] = s;     // never true; keeps the chains alive
+}
+cudaError_t launch_dfma_probe(double *sink, int iters, int blocks, cudaStream_t stream)
+{
+    dfma_probe_kernel<<<blocks, 256, 0, stream>>>(sink, iters);
+    return cudaGetLastError();
+}
+
+// ---- field handle -----------------------------------------------------------
+struct DeviceFields {
+    int dev = -1;
+    BathyDev b{};
+    CurrentDev c{};
+    std::vector<void *> allocs;
+};
+
+}  // namespace mr
+
+struct mr_fields {
+    uint32_t mask = 0;
+    std::vector<mr::DeviceFields> devs;
+    std::mutex mu;      // one trace at a time per handle and device set
+};
+
+struct mr_nc3 {
+    mr::Nc3File file;
+};
+
+namespace mr {
+
+static int device_count_quiet()
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+    return n;
+}
+
+template <typename T>
+static int upload(DeviceFields &d, const T *host, size_t count, const T **out)
+{
+    void *p = nullptr;
+    MR_CUDA(cudaMalloc(&p, count * sizeof(T)));
+    d.allocs.push_back(p);
+    MR_CUDA(cudaMemcpy(p, host, count * sizeof(T), cudaMemcpyHostToDevice));
+    *out = (const T *)p;
+    return MR_OK;
+}
+
+static int validate(const mr_bathymetry_desc *b, const mr_current_desc *c)
+{
+    if (!b || !c) return fail(MR_ERR_BAD_ARG, "mr_fields_create: NULL descriptor");
+    switch (b->kind) {
+    case MR_BATHY_CONSTANT: case MR_BATHY_SLOPE: break;
+    case MR_BATHY_GRID:
+        if (b->nx < 2 || b->ny < 2) return fail(MR_ERR_BAD_ARG, "bathymetry grid needs nx >= 2 and ny >= 2");
+        if (!b->x || !b->y || !b->depth) return fail(MR_ERR_BAD_ARG, "bathymetry grid: NULL x / y / depth");
+        {
+            float sx = fabsf(b->x[1] - b->x[0]), sy = fabsf(b->y[1] - b->y[0]);
+            if (!(sx > 0.0f) || !(sy > 0.0f) || std::isinf(sx) || std::isinf(sy))
+                return fail(MR_ERR_BAD_ARG, "bathymetry grid: x[1]-x[0] and y[1]-y[0] must be finite and non-zero");
+        }
+        break;
+    case MR_BATHY_ARRAY:
+        if (b->nx < 1 || b->ny < b->nx || !b->array)
+            return fail(MR_ERR_BAD_ARG, "bathymetry array needs nx >= 1, ny >= nx and a non-NULL array");
+        break;
+    default: return fail(MR_ERR_BAD_ARG, "unknown bathymetry kind");
+    }
+    switch (c->kind) {
+    case MR_CURRENT_CONSTANT: break;
+    case MR_CURRENT_GRID:
+        if (c->nx < 2 || c->ny < 2) return fail(MR_ERR_BAD_ARG, "current grid needs nx >= 2 and ny >= 2");
+        if (!c->x || !c->y || !c->u || !c->v) return fail(MR_ERR_BAD_ARG, "current grid: NULL x / y / u / v");
+        {
+            double sx = fabs(c->x[1] - c->x[0]), sy = fabs(c->y[1] - c->y[0]);
+            if (!(sx > 0.0) || !(sy > 0.0) || std::isinf(sx) || std::isinf(sy))
+                return fail(MR_ERR_BAD_ARG, "current grid: x[1]-x[0] and y[1]-y[0] must be finite and non-zero");
+        }
+        break;
+    default: return fail(MR_ERR_BAD_ARG, "unknown current kind");
+    }
+    return MR_OK;
+}
+
+static int upload_fields(DeviceFields &d, const mr_bathymetry_desc *b, const mr_current_desc *c)
+{
+    MR_CUDA(cudaSetDevice(d.dev));
+    BathyDev &B = d.b;
+    B.kind = b->kind; B.nx = b->nx; B.ny = b->ny;
+    B.h0 = b->h0; B.x0 = b->x0; B.y0 = b->y0; B.dhdx = b->dhdx; B.dhdy = b->dhdy;
+    if (b->kind == MR_BATHY_GRID) {
+        int rc;
+        if ((rc = upload(d, b->x, (size_t)b->nx, &B.x))) return rc;
+        if ((rc = upload(d, b->y, (size_t)b->ny, &B.y))) return rc;
+        if ((rc = upload(d, b->depth, (size_t)b->nx * b->ny, &B.depth))) return rc;
+        B.xf0 = b->x[0]; B.yf0 = b->y[0];
+        B.sx = fabsf(b->x[1] - b->x[0]);                       // cartesian_netcdf3.rs:287
+        B.sy = fabsf(b->y[1] - b->y[0]);
+        B.x_space = (double)b->x[1] - (double)b->x[0];         // :119
+        B.y_space = (double)b->y[1] - (double)b->y[0];         // :120
+        B.inv_x_space = 1.0 / B.x_space;
+        B.inv_y_space = 1.0 / B.y_space;
+    } else if (b->kind == MR_BATHY_ARRAY) {
+        int rc;
+        if ((rc = upload(d, b->array, (size_t)b->nx * b->ny, &B.array))) return rc;
+    }
+    CurrentDev &C = d.c;
+    C.kind = c->kind; C.nx = c->nx; C.ny = c->ny; C.u0 = c->u0; C.v0 = c->v0;
+    if (c->kind == MR_CURRENT_GRID) {
+        int rc;
+        if ((rc = upload(d, c->x, (size_t)c->nx, &C.x))) return rc;
+        if ((rc = upload(d, c->y, (size_t)c->ny, &C.y))) return rc;
+        if ((rc = upload(d, c->u, (size_t)c->nx * c->ny, &C.u))) return rc;
+        if ((rc = upload(d, c->v, (size_t)c->nx * c->ny, &C.v))) return rc;
+        C.xd0 = c->x[0]; C.yd0 = c->y[0];
+        C.sx = fabs(c->x[1] - c->x[0]);                        // cartesian_current.rs:244
+        C.sy = fabs(c->y[1] - c->y[0]);
+        C.inv_sx = 1.0 / C.sx; C.inv_sy = 1.0 / C.sy;
+        C.x_space = c->x[1] - c->x[0];                         // :515
+        C.y_space = c->y[1] - c->y[0];                         // :516
+        C.inv_x_space = 1.0 / C.x_space;
+        C.inv_y_space = 1.0 / C.y_space;
+    }
+    return MR_OK;
+}
+
+static void free_device_fields(DeviceFields &d)
+{
+    if (d.dev >= 0 && !d.allocs.empty()) {
+        cudaSetDevice(d.dev);
+        for (void *p : d.allocs) cudaFree(p);
+    }
+    d.allocs.clear();
+}
+
+static const DeviceFields *find_device(const mr_fields *f, int dev)
+{
+    for (auto &d : f->devs) if (d.dev == dev) return &d;
+    return nullptr;
+}
+
+static void normalise_opts(const mr_trace_opts *in, mr_trace_opts &o)
+{
+    o = mr_trace_opts{1, MR_MATH_FAST, 0, 0};
+    if (in) o = *in;
+    if (o.stride <= 0) o.stride = 1;
+}
+
+static int enqueue_trace(const DeviceFields &d, cudaStream_t stream, int64_t n,
+                         const double *x0, const double *y0, const double *kx0, const double *ky0,
+                         double dt, int64_t nsteps, const mr_trace_opts &o,
+                         double *x, double *y, double *kx, double *ky, int64_t ld,
+                         int32_t *rows, int32_t *len, double *fin)
+{
+    TraceArgs a;
+    a.b = d.b; a.c = d.c; a.n = n;
+    a.x0 = x0; a.y0 = y0; a.kx0 = kx0; a.ky0 = ky0;
+    a.dt = dt; a.nsteps = nsteps; a.stride = o.stride;
+    a.x = x; a.y = y; a.kx = kx; a.ky = ky; a.ld = ld;
+    a.rows = rows; a.len = len; a.fin = fin;
+    cudaError_t e;
+    if (o.math == MR_MATH_STRICT) e = launch_trace_strict(a, stream);
+    else if (o.math == MR_MATH_FAST) e = launch_trace_fast(a, stream);
+    else return fail(MR_ERR_BAD_ARG, "mr_trace_opts.math must be MR_MATH_FAST or MR_MATH_STRICT");
+    if (e != cudaSuccess) return cuda_fail(e, "trace kernel launch");
+    return MR_OK;
+}
+
+// ---- host-buffer path: one device's share --------------------------------------
+struct HostJob {
+    int64_t n_total;
+    const double *x0, *y0, *kx0, *ky0;
+    double dt; int64_t nsteps; int64_t rows_cap;
+    mr_trace_opts o;
+    double *x, *y, *kx, *ky;
+    int32_t *rows, *len; double *fin;
+};
+
+struct DevBuf {
+    double *ic = nullptr;        // [4][chunk] initial conditions
+    double *traj = nullptr;      // [4][rows_cap][chunk]
+    int32_t *rows = nullptr, *len = nullptr;
+    double *fin = nullptr;       // [4][chunk]
+    cudaEvent_t computed = nullptr, drained = nullptr;
+};
+
+static void free_devbuf(DevBuf &b)
+{
+    cudaFree(b.ic); cudaFree(b.traj); cudaFree(b.rows); cudaFree(b.len); cudaFree(b.fin);
+    if (b.computed) cudaEventDestroy(b.computed);
+    if (b.drained) cudaEventDestroy(b.drained);
+    b = DevBuf{};
+}
+
+// Traces rays [lo, hi) on device d.  Rays are cut into slabs of `chunk` rays;
+// slab k+1 integrates on the compute stream while slab k drains to the host on
+// the copy stream (two device buffers).
+static int trace_block_on_device(const DeviceFields &d, const HostJob &j, int64_t lo, int64_t hi, std::string &err)
+{
+    auto bail = [&](int code, const std::string &m) { err = m; return code; };
+#define MR_TRY(call)                                                                      \
+    do {                                                                                  \
+        cudaError_t e__ = (call);                                                         \
+        if (e__ != cudaSuccess) {                                                         \
+            rc = bail(e__ == cudaErrorMemoryAllocation ? MR_ERR_OOM : MR_ERR_CUDA,        \
+                      std::string(#call) + ": " + cudaGetErrorString(e__));               \
+            goto done;                                                                    \
+        }                                                                                 \
+    } while (0)
+
+    int rc = MR_OK;
+    const int64_t n = hi - lo;
+    if (n <= 0) return MR_OK;
+    const bool want_traj = j.x || j.y || j.kx || j.ky;
+    cudaStream_t s_comp = nullptr, s_copy = nullptr;
+    DevBuf buf[2];
+    int nbuf = 1;
+    int64_t chunk = n;
+    {
+        cudaError_t e = cudaSetDevice(d.dev);
+        if (e != cudaSuccess) return bail(MR_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+    }
+    {
+        size_t free_b = 0, total_b = 0;
+        MR_TRY(cudaMemGetInfo(&free_b, &total_b));
+        // bytes one ray needs on the device
+        const double per_ray = 32.0 + (want_traj ? 32.0 * (double)j.rows_cap : 0.0) + 8.0 + 32.0;
+        double budget = 0.80 * (double)free_b;
+        if (j.o.chunk_rays > 0) {
+            chunk = std::min<int64_t>(n, j.o.chunk_rays);
+        } else if (per_ray * (double)n > budget || (want_traj && per_ray * (double)n > 4e9)) {
+            // does not fit, or is big enough that overlapping the drain with the next
+            // slab's integration pays: two slabs in flight
+            const double cap = std::min(budget / 2.0, 16e9);
+            const int64_t wave = 148 * 4 * kBlock;          // rays that fill the machine once
+            chunk = (int64_t)(cap / per_ray);
+            if (chunk >= wave) chunk = chunk / wave * wave;
+            chunk = std::max<int64_t>(std::min(chunk, n), 1);
+        }
+        nbuf = chunk < n ? 2 : 1;
+    }
+    MR_TRY(cudaStreamCreateWithFlags(&s_comp, cudaStreamNonBlocking));
+    MR_TRY(cudaStreamCreateWithFlags(&s_copy, cudaStreamNonBlocking));
+    for (int b = 0; b < nbuf; ++b) {
+        MR_TRY(cudaMalloc(&buf[b].ic, sizeof(double) * 4 * (size_t)chunk));
+        if (want_traj) MR_TRY(cudaMalloc(&buf[b].traj, sizeof(double) * 4 * (size_t)j.rows_cap * (size_t)chunk));
+        MR_TRY(cudaMalloc(&buf[b].rows, sizeof(int32_t) * (size_t)chunk));
+        MR_TRY(cudaMalloc(&buf[b].len, sizeof(int32_t) * (size_t)chunk));
+        if (j.fin) MR_TRY(cudaMalloc(&buf[b].fin, sizeof(double) * 4 * (size_t)chunk));
+        MR_TRY(cudaEventCreateWithFlags(&buf[b].computed, cudaEventDisableTiming));
+        MR_TRY(cudaEventCreateWithFlags(&buf[b].drained, cudaEventDisableTiming));
+    }
+    {
+        int k = 0;
+        for (int64_t c0 = lo; c0 < hi; c0 += chunk, ++k) {
+            DevBuf &B = buf[k % nbuf];
+            const int64_t m = std::min(chunk, hi - c0);
+            if (k >= nbuf) MR_TRY(cudaStreamWaitEvent(s_comp, B.drained, 0));
+            MR_TRY(cudaMemcpyAsync(B.ic,             j.x0  + c0, sizeof(double) * m, cudaMemcpyHostToDevice, s_comp));
+            MR_TRY(cudaMemcpyAsync(B.ic + chunk,     j.y0  + c0, sizeof(double) * m, cudaMemcpyHostToDevice, s_comp));
+            MR_TRY(cudaMemcpyAsync(B.ic + 2 * chunk, j.kx0 + c0, sizeof(double) * m, cudaMemcpyHostToDevice, s_comp));
+            MR_TRY(cudaMemcpyAsync(B.ic + 3 * chunk, j.ky0 + c0, sizeof(double) * m, cudaMemcpyHostToDevice, s_comp));
+            const size_t plane = (size_t)j.rows_cap * (size_t)chunk;
+            double *tx = want_traj ? B.traj : nullptr;
+            {
+                TraceArgs a;
+                a.b = d.b; a.c = d.c; a.n = m;
+                a.x0 = B.ic; a.y0 = B.ic + chunk; a.kx0 = B.ic + 2 * chunk; a.ky0 = B.ic + 3 * chunk;
+                a.dt = j.dt; a.nsteps = j.nsteps; a.stride = j.o.stride;
+                a.x = tx; a.y = tx ? tx + plane : nullptr; a.kx = tx ? tx + 2 * plane : nullptr; a.ky = tx ? tx + 3 * plane : nullptr;
+                a.ld = chunk;
+                a.rows = B.rows; a.len = B.len; a.fin = B.fin;
+                // fin is [4][n] with n = m for the kernel (it uses a.n as the pitch)
+                cudaError_t e = j.o.math == MR_MATH_STRICT ? launch_trace_strict(a, s_comp) : launch_trace_fast(a, s_comp);
+                if (e != cudaSuccess) { rc = bail(MR_ERR_CUDA, std::string("trace kernel launch: ") + cudaGetErrorString(e)); goto done; }
+            }
+            MR_TRY(cudaEventRecord(B.computed, s_comp));
+            MR_TRY(cudaStreamWaitEvent(s_copy, B.computed, 0));
+            if (want_traj) {
+                double *dsts[4] = { j.x, j.y, j.kx, j.ky };
+                for (int f = 0; f < 4; ++f) {
+                    if (!dsts[f]) continue;
+                    MR_TRY(cudaMemcpy2DAsync(dsts[f] + c0, sizeof(double) * (size_t)j.n_total,
+                                             B.traj + f * plane, sizeof(double) * (size_t)chunk,
+                                             sizeof(double) * (size_t)m, (size_t)j.rows_cap,
+                                             cudaMemcpyDeviceToHost, s_copy));
+                }
+            }
+            if (j.rows) MR_TRY(cudaMemcpyAsync(j.rows + c0, B.rows, sizeof(int32_t) * m, cudaMemcpyDeviceToHost, s_copy));
+            if (j.len)  MR_TRY(cudaMemcpyAsync(j.len + c0,  B.len,  sizeof(int32_t) * m, cudaMemcpyDeviceToHost, s_copy));
+            if (j.fin) {
+                for (int f = 0; f < 4; ++f)
+                    MR_TRY(cudaMemcpyAsync(j.fin + (size_t)f * j.n_total + c0, B.fin + (size_t)f * m,
+                                           sizeof(double) * m, cudaMemcpyDeviceToHost, s_copy));
+            }
+            MR_TRY(cudaEventRecord(B.drained, s_copy));
+        }
+    }
+    MR_TRY(cudaStreamSynchronize(s_comp));
+    MR_TRY(cudaStreamSynchronize(s_copy));
+done:
+    if (rc != MR_OK) cudaDeviceSynchronize();
+    for (int b = 0; b < 2; ++b) free_devbuf(buf[b]);
+    if (s_comp) cudaStreamDestroy(s_comp);
+    if (s_copy) cudaStreamDestroy(s_copy);
+    if (rc != MR_OK) (void)cudaGetLastError();
+    return rc;
+#undef MR_TRY
+}
+
+}  // namespace mr
+
+using namespace mr;
+
+// =============================================================================
+// C ABI
+// =============================================================================
+extern "C" {
+
+int mr_abi_version(void) { return MR_ABI_VERSION; }
+int mr_device_count(void) { return device_count_quiet(); }
+const char *mr_last_error(void) { return g_err.c_str(); }
+
+int mr_fields_create(const mr_bathymetry_desc *bathy, const mr_current_desc *current,
+                     uint32_t device_mask, mr_fields **out)
+{
+    if (!out) return fail(MR_ERR_BAD_ARG, "mr_fields_create: out is NULL");
+    *out = nullptr;
+    int rc = validate(bathy, current);
+    if (rc) return rc;
+    int ndev = device_count_quiet();
+    if (ndev <= 0) return fail(MR_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+    if (device_mask == 0) device_mask = 1u;
+    for (int i = 0; i < 32; ++i)
+        if ((device_mask >> i & 1u) && i >= ndev)
+            return fail(MR_ERR_BAD_ARG, "device_mask selects device " + std::to_string(i) + " but only " +
+                                            std::to_string(ndev) + " device(s) are visible");
+    std::unique_ptr<mr_fields> f(new (std::nothrow) mr_fields);
+    if (!f) return fail(MR_ERR_OOM, "out of host memory");
+    f->mask = device_mask;
+    for (int i = 0; i < 32; ++i) {
+        if (!(device_mask >> i & 1u)) continue;
+        f->devs.emplace_back();
+        f->devs.back().dev = i;
+        rc = upload_fields(f->devs.back(), bathy, current);
+        if (rc) {
+            for (auto &d : f->devs) free_device_fields(d);
+            return rc;
+        }
+    }
+    *out = f.release();
+    return MR_OK;
+}
+
+int mr_fields_open_netcdf3(const char *bathymetry_path, const char *current_path,
+                           uint32_t device_mask, mr_fields **out)
+{
+    if (!out) return fail(MR_ERR_BAD_ARG, "mr_fields_open_netcdf3: out is NULL");
+    *out = nullptr;
+    std::string err;
+    std::vector<float> bx, by;
+    std::vector<double> depth, cx, cy, cu, cv;
+    mr_bathymetry_desc b{};
+    mr_current_desc c{};
+    if (bathymetry_path) {
+        // CartesianNetcdf3::open(path, "x", "y", "depth")  src/ffi.rs:36, :62
+        Nc3File f;
+        int rc = Nc3File::open(bathymetry_path, f, err);
+        if (rc) return fail(rc, "could not open bathymetry file: " + err);
+        if ((rc = f.read_f32("x", bx, err)) || (rc = f.read_f32("y", by, err)) || (rc = f.read_f64("depth", depth, err)))
+            return fail(rc, "could not open bathymetry file: " + err);
+        if (bx.size() > (size_t)INT32_MAX || by.size() > (size_t)INT32_MAX)
+            return fail(MR_ERR_FORMAT, "bathymetry coordinates too long");
+        if (depth.size() != bx.size() * by.size())
+            return fail(MR_ERR_FORMAT, "bathymetry file: depth has " + std::to_string(depth.size()) + " values, expected len(x)*len(y) = " +
+                                           std::to_string(bx.size() * by.size()));
+        b.kind = MR_BATHY_GRID; b.nx = (int32_t)bx.size(); b.ny = (int32_t)by.size();
+        b.x = bx.data(); b.y = by.data(); b.depth = depth.data();
+    } else {
+        b.kind = MR_BATHY_CONSTANT; b.h0 = 2000.0f;          // DEFAULT_BATHYMETRY constant_depth.rs:9
+    }
+    if (current_path) {
+        // CartesianCurrent::open(path, "x", "y", "u", "v")  src/ffi.rs:38, :64
+        Nc3File f;
+        int rc = Nc3File::open(current_path, f, err);
+        if (rc) return fail(rc, "could not open current file: " + err);
+        if ((rc = f.read_f64("x", cx, err)) || (rc = f.read_f64("y", cy, err)) ||
+            (rc = f.read_f64("u", cu, err)) || (rc = f.read_f64("v", cv, err)))
+            return fail(rc, "could not open current file: " + err);
+        if (cx.size() > (size_t)INT32_MAX || cy.size() > (size_t)INT32_MAX)
+            return fail(MR_ERR_FORMAT, "current coordinates too long");
+        if (cu.size() != cx.size() * cy.size() || cv.size() != cx.size() * cy.size())
+            return fail(MR_ERR_FORMAT, "current file: u/v do not have len(x)*len(y) values");
+        c.kind = MR_CURRENT_GRID; c.nx = (int32_t)cx.size(); c.ny = (int32_t)cy.size();
+        c.x = cx.data(); c.y = cy.data(); c.u = cu.data(); c.v = cv.data();
+    } else {
+        c.kind = MR_CURRENT_CONSTANT; c.u0 = 0.0; c.v0 = 0.0;  // DEFAULT_CURRENT constant_current.rs:10
+    }
+    return mr_fields_create(&b, &c, device_mask, out);
+}
+
+void mr_fields_free(mr_fields *f)
+{
+    if (!f) return;
+    for (auto &d : f->devs) free_device_fields(d);
+    delete f;
+}
+
+uint32_t mr_fields_device_mask(const mr_fields *f) { return f ? f->mask : 0; }
+
+int64_t mr_num_steps(double t0, double t_end, double dt)
+{
+    if (!(dt > 0.0)) return -1;
+    double q = std::ceil((t_end - t0) / dt);
+    if (!(q >= 0.0) || !(q < 2147483646.0)) return -1;
+    return (int64_t)q;
+}
+
+int64_t mr_num_rows(double t0, double t_end, double dt, int32_t stride)
+{
+    int64_t n = mr_num_steps(t0, t_end, dt);
+    if (n < 0) return -1;
+    if (stride <= 0) stride = 1;
+    return n / stride + 1;
+}
+
+static void fill_time(double *t, double t0, double dt, int64_t nsteps, int32_t stride)
+{
+    if (!t) return;
+    double tt = t0;
+    t[0] = tt;
+    for (int64_t s = 1; s <= nsteps; ++s) {
+        tt = tt + dt;                  // x_new = x + h, accumulated (ode_solvers Rk4::step)
+        if (s % stride == 0) t[s / stride] = tt;
+    }
+}
+
+int mr_trace_many(mr_fields *f, int64_t n,
+                  const double *x0, const double *y0, const double *kx0, const double *ky0,
+                  double t0, double t_end, double dt, const mr_trace_opts *opts,
+                  double *t, double *x, double *y, double *kx, double *ky,
+                  int32_t *rows, int32_t *len, double *final_state)
+{
+    if (!f) return fail(MR_ERR_BAD_ARG, "mr_trace_many: NULL field handle");
+    if (n < 0) return fail(MR_ERR_BAD_ARG, "mr_trace_many: n < 0");
+    if (n > 0 && (!x0 || !y0 || !kx0 || !ky0)) return fail(MR_ERR_BAD_ARG, "mr_trace_many: NULL initial-condition array");
+    mr_trace_opts o;
+    normalise_opts(opts, o);
+    if (o.math != MR_MATH_FAST && o.math != MR_MATH_STRICT) return fail(MR_ERR_BAD_ARG, "mr_trace_opts.math must be MR_MATH_FAST or MR_MATH_STRICT");
+    const int64_t nsteps = mr_num_steps(t0, t_end, dt);
+    if (nsteps < 0) return fail(MR_ERR_BAD_ARG, "mr_trace_many: need dt > 0 and 0 <= (t_end - t0)/dt < 2^31 (the reference panics here)");
+    const bool any_traj = x || y || kx || ky;
+    if (any_traj && !(x && y && kx && ky)) return fail(MR_ERR_BAD_ARG, "mr_trace_many: pass all four of x, y, kx, ky or none");
+    fill_time(t, t0, dt, nsteps, o.stride);
+    if (n == 0) return MR_OK;
+
+    HostJob j;
+    j.n_total = n; j.x0 = x0; j.y0 = y0; j.kx0 = kx0; j.ky0 = ky0;
+    j.dt = dt; j.nsteps = nsteps; j.rows_cap = nsteps / o.stride + 1; j.o = o;
+    j.x = x; j.y = y; j.kx = kx; j.ky = ky; j.rows = rows; j.len = len; j.fin = final_state;
+
+    std::lock_guard<std::mutex> guard(f->mu);
+    const int G = (int)f->devs.size();
+    // contiguous blocks of rays per device, rounded to whole thread blocks
+    int64_t per = (n + G - 1) / G;
+    per = (per + kBlock - 1) / kBlock * kBlock;
+    std::vector<int> rcs(G, MR_OK);
+    std::vector<std::string> errs(G);
+    if (G == 1) {
+        rcs[0] = trace_block_on_device(f->devs[0], j, 0, n, errs[0]);
+    } else {
+        std::vector<std::thread> th;
+        for (int g = 0; g < G; ++g) {
+            int64_t lo = std::min<int64_t>((int64_t)g * per, n), hi = std::min<int64_t>(lo + per, n);
+            th.emplace_back([&, g, lo, hi] { rcs[g] = trace_block_on_device(f->devs[g], j, lo, hi, errs[g]); });
+        }
+        for (auto &t_ : th) t_.join();
+    }
+    for (int g = 0; g < G; ++g)
+        if (rcs[g] != MR_OK) return fail(rcs[g], "device " + std::to_string(f->devs[g].dev) + ": " + errs[g]);
+    return MR_OK;
+}
+
+int mr_single_ray(mr_fields *f, double x0, double y0, double kx0, double ky0,
+                  double t0, double t_end, double dt, const mr_trace_opts *opts,
+                  double *out, int64_t out_cap, int64_t *n_rows)
+{
+    if (!f || !n_rows) return fail(MR_ERR_BAD_ARG, "mr_single_ray: NULL argument");
+    mr_trace_opts o;
+    normalise_opts(opts, o);
+    if (o.stride != 1) return fail(MR_ERR_BAD_ARG, "mr_single_ray: stride must be 1");
+    const int64_t nsteps = mr_num_steps(t0, t_end, dt);
+    if (nsteps < 0) return fail(MR_ERR_BAD_ARG, "mr_single_ray: need dt > 0 and 0 <= (t_end - t0)/dt < 2^31 (the reference panics here)");
+    const int64_t cap = nsteps + 1;
+    std::vector<double> t((size_t)cap), soa((size_t)cap * 4);
+    int32_t rows = 0;
+    // restrict to the first device of the handle: a single ray cannot be sharded
+    mr_fields one;
+    one.mask = 1u << f->devs[0].dev;
+    one.devs.push_back(f->devs[0]);
+    int rc = mr_trace_many(&one, 1, &x0, &y0, &kx0, &ky0, t0, t_end, dt, &o, t.data(),
+                           soa.data(), soa.data() + cap, soa.data() + 2 * cap, soa.data() + 3 * cap,
+                           &rows, nullptr, nullptr);
+    one.devs.clear();                       // borrowed, not owned
+    if (rc) return rc;
+    *n_rows = rows;
+    if (rows > out_cap || !out) return fail(MR_ERR_BAD_ARG, "mr_single_ray: out holds " + std::to_string(out_cap) +
+                                                        " rows, " + std::to_string(rows) + " needed");
+    for (int64_t r = 0; r < rows; ++r) {    // (t, x, y, kx, ky) tuples, src/ffi.rs:42-47
+        out[5 * r + 0] = t[(size_t)r];
+        for (int c = 0; c < 4; ++c) out[5 * r + 1 + c] = soa[(size_t)c * cap + r];
+    }
+    return MR_OK;
+}
+
+int mr_trace_device(mr_fields *f, int device, void *stream, int64_t n,
+                    const double *d_x0, const double *d_y0, const double *d_kx0, const double *d_ky0,
+                    double t0, double t_end, double dt, const mr_trace_opts *opts,
+                    double *d_x, double *d_y, double *d_kx, double *d_ky, int64_t ld,
+                    int32_t *d_rows, int32_t *d_len, double *d_final, int32_t *launches)
+{
+    if (launches) *launches = 0;
+    if (!f) return fail(MR_ERR_BAD_ARG, "mr_trace_device: NULL field handle");
+    const DeviceFields *d = find_device(f, device);
+    if (!d) return fail(MR_ERR_BAD_ARG, "mr_trace_device: device " + std::to_string(device) + " is not in the handle's mask");
+    if (n < 0) return fail(MR_ERR_BAD_ARG, "mr_trace_device: n < 0");
+    if (n > 0 && (!d_x0 || !d_y0 || !d_kx0 || !d_ky0)) return fail(MR_ERR_BAD_ARG, "mr_trace_device: NULL initial-condition array");
+    mr_trace_opts o;
+    normalise_opts(opts, o);
+    const int64_t nsteps = mr_num_steps(t0, t_end, dt);
+    if (nsteps < 0) return fail(MR_ERR_BAD_ARG, "mr_trace_device: need dt > 0 and 0 <= (t_end - t0)/dt < 2^31");
+    const bool any_traj = d_x || d_y || d_kx || d_ky;
+    if (any_traj && !(d_x && d_y && d_kx && d_ky)) return fail(MR_ERR_BAD_ARG, "mr_trace_device: pass all four of x, y, kx, ky or none");
+    if (any_traj && ld < n) return fail(MR_ERR_BAD_ARG, "mr_trace_device: ld < n");
+    if (n == 0) return MR_OK;
+    int cur = -1;
+    MR_CUDA(cudaGetDevice(&cur));
+    if (cur != device) MR_CUDA(cudaSetDevice(device));
+    int rc = enqueue_trace(*d, (cudaStream_t)stream, n, d_x0, d_y0, d_kx0, d_ky0, dt, nsteps, o,
+                           d_x, d_y, d_kx, d_ky, ld, d_rows, d_len, d_final);
+    if (cur != device) cudaSetDevice(cur);
+    if (rc == MR_OK && launches) *launches = 1;
+    return rc;
+}
+
+int mr_measure_fp64_peak(int device, int millis, double *tflops)
+{
+    if (!tflops) return fail(MR_ERR_BAD_ARG, "mr_measure_fp64_peak: NULL output");
+    *tflops = 0.0;
+    if (device < 0 || device >= device_count_quiet()) return fail(MR_ERR_CUDA, "mr_measure_fp64_peak: no such CUDA device");
+    int cur = -1;
+    MR_CUDA(cudaGetDevice(&cur));
+    MR_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    MR_CUDA(cudaGetDeviceProperties(&prop, device));
+    double *sink = nullptr;
+    MR_CUDA(cudaMalloc(&sink, sizeof(double)));
+    cudaEvent_t e0, e1;
+    MR_CUDA(cudaEventCreate(&e0));
+    MR_CUDA(cudaEventCreate(&e1));
+    const int blocks = prop.multiProcessorCount * 8;
+    int iters = 2000;
+    double best = 0.0;
+    float ms = 0.f;
+    // warm up, then size the loop for ~millis of work
+    MR_CUDA(launch_dfma_probe(sink, iters, blocks, 0));
+    MR_CUDA(cudaDeviceSynchronize());
+    for (int rep = 0; rep < 4; ++rep) {
+        MR_CUDA(cudaEventRecord(e0, 0));
+        MR_CUDA(launch_dfma_probe(sink, iters, blocks, 0));
+        MR_CUDA(cudaEventRecord(e1, 0));
+        MR_CUDA(cudaEventSynchronize(e1));
+        MR_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        double flops = 2.0 * 64.0 * (double)iters * 256.0 * (double)blocks;
+        double tf = flops / ((double)ms * 1e-3) / 1e12;
+        if (rep > 0) best = std::max(best, tf);
+        if (rep == 0 && ms > 0.f && millis > 0) {
+            double scale = (double)millis / ms;
+            iters = (int)std::min(2e6, std::max(200.0, iters * scale));
+        }
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    if (cur != device) cudaSetDevice(cur);
+    *tflops = best;
+    return MR_OK;
+}
+
+// ---- NetCDF-3 ---------------------------------------------------------------
+int mr_nc3_open(const char *path, mr_nc3 **out)
+{
+    if (!path || !out) return fail(MR_ERR_BAD_ARG, "mr_nc3_open: NULL argument");
+    *out = nullptr;
+    std::unique_ptr<mr_nc3> h(new (std::nothrow) mr_nc3);
+    if (!h) return fail(MR_ERR_OOM, "out of host memory");
+    std::string err;
+    int rc = Nc3File::open(path, h->file, err);
+    if (rc) return fail(rc, err);
+    *out = h.release();
+    return MR_OK;
+}
+void mr_nc3_close(mr_nc3 *f) { delete f; }
+int mr_nc3_var_count(const mr_nc3 *f) { return f ? (int)f->file.vars.size() : 0; }
+int mr_nc3_var_name(const mr_nc3 *f, int index, char *buf, size_t cap)
+{
+    if (!f || !buf || cap == 0 || index < 0 || index >= (int)f->file.vars.size()) return fail(MR_ERR_BAD_ARG, "mr_nc3_var_name: bad argument");
+    std::strncpy(buf, f->file.vars[(size_t)index].name.c_str(), cap - 1);
+    buf[cap - 1] = 0;
+    return MR_OK;
+}
+int mr_nc3_var_info(const mr_nc3 *f, const char *name, int32_t *nc_type, int64_t *n_elems, int32_t *ndims, int64_t dims[MR_NC3_MAX_DIMS])
+{
+    if (!f || !name) return fail(MR_ERR_BAD_ARG, "mr_nc3_var_info: NULL argument");
+    const Nc3Var *v = f->file.find(name);
+    if (!v) return fail(MR_ERR_FORMAT, "'" + f->file.path + "': no variable named '" + name + "'");
+    if (nc_type) *nc_type = v->type;
+    if (n_elems) *n_elems = (int64_t)f->file.num_elems(*v);
+    if (ndims) *ndims = (int32_t)v->dimids.size();
+    if (dims)
+        for (size_t k = 0; k < v->dimids.size() && k < MR_NC3_MAX_DIMS; ++k) {
+            uint32_t l = f->file.dims[v->dimids[k]].len;
+            dims[k] = (k == 0 && v->is_record) ? (int64_t)f->file.numrecs : (int64_t)l;
+        }
+    return MR_OK;
+}
+int mr_nc3_read_f32(const mr_nc3 *f, const char *name, float *out, int64_t cap)
+{
+    if (!f || !name || !out) return fail(MR_ERR_BAD_ARG, "mr_nc3_read_f32: NULL argument");
+    std::vector<float> v;
+    std::string err;
+    int rc = f->file.read_f32(name, v, err);
+    if (rc) return fail(rc, err);
+    if ((int64_t)v.size() > cap) return fail(MR_ERR_BAD_ARG, "mr_nc3_read_f32: buffer too small");
+    std::memcpy(out, v.data(), v.size() * sizeof(float));
+    return MR_OK;
+}
+int mr_nc3_read_f64(const mr_nc3 *f, const char *name, double *out, int64_t cap)
+{
+    if (!f || !name || !out) return fail(MR_ERR_BAD_ARG, "mr_nc3_read_f64: NULL argument");
+    std::vector<double> v;
+    std::string err;
+    int rc = f->file.read_f64(name, v, err);
+    if (rc) return fail(rc, err);
+    if ((int64_t)v.size() > cap) return fail(MR_ERR_BAD_ARG, "mr_nc3_read_f64: buffer too small");
+    std::memcpy(out, v.data(), v.size() * sizeof(double));
+    return MR_OK;
+}
+
+// ---- pinned host memory -------------------------------------------------------
+int mr_host_alloc(size_t bytes, void **out)
+{
+    if (!out) return fail(MR_ERR_BAD_ARG, "mr_host_alloc: NULL out");
+    *out = nullptr;
+    if (device_count_quiet() <= 0) return fail(MR_ERR_CUDA, "no CUDA device available");
+    cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); *out = nullptr; return cuda_fail(e, "cudaHostAlloc"); }
+    return MR_OK;
+}
+void mr_host_free(void *p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+}  // extern "C"

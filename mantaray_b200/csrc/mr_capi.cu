@@ -144,6 +144,76 @@ static int validate(const mr_bathymetry_desc *b, const mr_current_desc *c)
     return MR_OK;
 }
 
+// ---- per-cell records of the fast path ----------------------------------------------
+// Built once at upload from the f64 node grids with exactly the reference's operations:
+// corner values `as f32` (cartesian_netcdf3.rs:426, cartesian_current.rs:378), gradients as
+// IEEE f64 quotients (cartesian_netcdf3.rs:126-134 then `as f32`; cartesian_current.rs:522-536).
+__global__ void build_bathy_cells(const double *depth, int nx, int ny, double x_space, double y_space, float4 *cell)
+{
+    const size_t ncell = (size_t)(nx - 1) * (ny - 1);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < ncell; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t x1 = i % (size_t)(nx - 1), y1 = i / (size_t)(nx - 1);
+        const double *p = depth + (size_t)nx * y1 + x1;
+        const double sw = p[0], se = p[1], nw = p[nx], ne = p[nx + 1];
+        cell[2 * i] = make_float4((float)sw, (float)nw, (float)ne, (float)se);
+        cell[2 * i + 1] = make_float4((float)__ddiv_rn(__dsub_rn(se, sw), x_space),
+                                      (float)__ddiv_rn(__dsub_rn(nw, sw), y_space), 0.0f, 0.0f);
+    }
+}
+
+__global__ void build_current_cells(const double *u, const double *v, int nx, int ny, double x_space, double y_space,
+                                    float4 *cell_uv, double2 *cell_grad)
+{
+    const size_t ncell = (size_t)(nx - 1) * (ny - 1);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < ncell; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t x1 = i % (size_t)(nx - 1), y1 = i / (size_t)(nx - 1);
+        const double *pu = u + (size_t)nx * y1 + x1, *pv = v + (size_t)nx * y1 + x1;
+        const double usw = pu[0], use_ = pu[1], unw = pu[nx], une = pu[nx + 1];
+        const double vsw = pv[0], vse = pv[1], vnw = pv[nx], vne = pv[nx + 1];
+        cell_uv[2 * i] = make_float4((float)usw, (float)unw, (float)une, (float)use_);
+        cell_uv[2 * i + 1] = make_float4((float)vsw, (float)vnw, (float)vne, (float)vse);
+        cell_grad[2 * i] = make_double2(__ddiv_rn(__dsub_rn(use_, usw), x_space), __ddiv_rn(__dsub_rn(unw, usw), y_space));
+        cell_grad[2 * i + 1] = make_double2(__ddiv_rn(__dsub_rn(vse, vsw), x_space), __ddiv_rn(__dsub_rn(vnw, vsw), y_space));
+    }
+}
+
+// Are the f32 coordinates exactly affine, i.e. does the kernel's own arithmetic
+// (xa = fmaf(i, d, c[0]); xb = xa + d) reproduce every c[i] bit for bit?
+static bool affine_f32(const float *c, int n, float *d_out)
+{
+    const float d = c[1] - c[0];
+    if (!(d > 0.0f) || std::isinf(d)) return false;
+    for (int i = 0; i < n; ++i) {
+        const float xa = std::fmaf((float)i, d, c[0]);
+        if (xa != c[i]) return false;
+        if (i + 1 < n && xa + d != c[i + 1]) return false;
+    }
+    *d_out = d;
+    return true;
+}
+
+// change-of-basis coefficients of interpolator.rs:64-72 for a (dx, dy) cell, in f32
+static bool basis_coeffs(float dx, float dy, float *c01, float *c10)
+{
+    volatile float p = dx * dy;
+    volatile float det = 0.0f - p;
+    if (det == 0.0f || std::isinf(det) || std::isnan(det)) return false;
+    volatile float a = dx / det, b = dy / det;
+    *c01 = -a;
+    *c10 = -b;
+    return std::isfinite(*c01) && std::isfinite(*c10);
+}
+
+template <typename T>
+static int device_alloc(DeviceFields &d, size_t count, T **out)
+{
+    void *p = nullptr;
+    MR_CUDA(cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)));
+    d.allocs.push_back(p);
+    *out = (T *)p;
+    return MR_OK;
+}
+
 static int upload_fields(DeviceFields &d, const mr_bathymetry_desc *b, const mr_current_desc *c)
 {
     MR_CUDA(cudaSetDevice(d.dev));
@@ -160,8 +230,14 @@ static int upload_fields(DeviceFields &d, const mr_bathymetry_desc *b, const mr_
         B.sy = fabsf(b->y[1] - b->y[0]);
         B.x_space = (double)b->x[1] - (double)b->x[0];         // :119
         B.y_space = (double)b->y[1] - (double)b->y[0];         // :120
-        B.inv_x_space = 1.0 / B.x_space;
-        B.inv_y_space = 1.0 / B.y_space;
+        float4 *cell = nullptr;
+        const size_t ncell = (size_t)(b->nx - 1) * (b->ny - 1);
+        if ((rc = device_alloc(d, 2 * ncell, &cell))) return rc;
+        build_bathy_cells<<<(unsigned)std::min<size_t>((ncell + 255) / 256, 148 * 16), 256>>>(B.depth, b->nx, b->ny, B.x_space, B.y_space, cell);
+        MR_CUDA(cudaGetLastError());
+        B.cell = cell;
+        B.uniform = affine_f32(b->x, b->nx, &B.dxf) && affine_f32(b->y, b->ny, &B.dyf) &&
+                    basis_coeffs(B.dxf, B.dyf, &B.c01, &B.c10);
     } else if (b->kind == MR_BATHY_ARRAY) {
         int rc;
         if ((rc = upload(d, b->array, (size_t)b->nx * b->ny, &B.array))) return rc;
@@ -180,9 +256,26 @@ static int upload_fields(DeviceFields &d, const mr_bathymetry_desc *b, const mr_
         C.inv_sx = 1.0 / C.sx; C.inv_sy = 1.0 / C.sy;
         C.x_space = c->x[1] - c->x[0];                         // :515
         C.y_space = c->y[1] - c->y[0];                         // :516
-        C.inv_x_space = 1.0 / C.x_space;
-        C.inv_y_space = 1.0 / C.y_space;
+        const size_t ncell = (size_t)(c->nx - 1) * (c->ny - 1);
+        float4 *cell_uv = nullptr;
+        double2 *cell_grad = nullptr;
+        if ((rc = device_alloc(d, 2 * ncell, &cell_uv))) return rc;
+        if ((rc = device_alloc(d, 2 * ncell, &cell_grad))) return rc;
+        build_current_cells<<<(unsigned)std::min<size_t>((ncell + 255) / 256, 148 * 16), 256>>>(C.u, C.v, c->nx, c->ny, C.x_space, C.y_space,
+                                                                                               cell_uv, cell_grad);
+        MR_CUDA(cudaGetLastError());
+        C.cell_uv = cell_uv;
+        C.cell_grad = cell_grad;
+        std::vector<float> xf((size_t)c->nx), yf((size_t)c->ny);   // `as f32`, cartesian_current.rs:375-376
+        for (int i = 0; i < c->nx; ++i) xf[(size_t)i] = (float)c->x[i];
+        for (int i = 0; i < c->ny; ++i) yf[(size_t)i] = (float)c->y[i];
+        if ((rc = upload(d, xf.data(), xf.size(), &C.xf))) return rc;
+        if ((rc = upload(d, yf.data(), yf.size(), &C.yf))) return rc;
+        C.xf0 = xf[0]; C.yf0 = yf[0];
+        C.uniform = affine_f32(xf.data(), c->nx, &C.dxf) && affine_f32(yf.data(), c->ny, &C.dyf) &&
+                    basis_coeffs(C.dxf, C.dyf, &C.c01, &C.c10);
     }
+    MR_CUDA(cudaDeviceSynchronize());
     return MR_OK;
 }
 

@@ -8,10 +8,18 @@
 //   group velocity     src/wave_ray_path.rs:177-188
 //   dk/dt              src/wave_ray_path.rs:207-216
 //
-// The f32 stages (position rounding, fractional index, cell choice, bilinear)
-// are VALUE-IDENTICAL to the reference in both math modes: every f32 operation
-// is an explicit round-to-nearest intrinsic so nvcc can never contract it.
-// Only the f64 stage differs between MR_MATH_STRICT and MR_MATH_FAST.
+// Two arithmetic modes (include/mantaray_b200.h):
+//   MR_MATH_STRICT  the reference's expression tree operation by operation, on the
+//                   f64 node grids exactly as the reference stores them.
+//   MR_MATH_FAST    the production path.  The f32 stages (position rounding,
+//                   fractional index, cell choice, bilinear) are VALUE-IDENTICAL to
+//                   the reference — every f32 operation is an explicit round-to-
+//                   nearest intrinsic that nvcc cannot contract — but they read
+//                   per-cell records precomputed at upload (corner values already
+//                   cast to f32, finite-difference gradients already divided), so an
+//                   RHS does no f64->f32 conversions of grid data and no divisions
+//                   by grid constants.  The f64 stage is restructured around one
+//                   exponential (see rhs_f64_fast).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -27,27 +35,39 @@ struct BathyDev {
     int32_t kind;
     int32_t nx, ny;
     const float  *x, *y;       // GRID coordinates (f32, as CartesianNetcdf3 holds them)
-    const double *depth;       // GRID [ny*nx]
+    const double *depth;       // GRID [ny*nx]                                  (strict path)
     const float  *array;       // ARRAY [nx*ny]
     float h0, x0, y0, dhdx, dhdy;
     // derived at upload (GRID)
     float  xf0, yf0;           // x[0], y[0]
     float  sx, sy;             // |x[1]-x[0]|, |y[1]-y[0]| in f32   (cartesian_netcdf3.rs:287)
     double x_space, y_space;   // x[1]-x[0] in f64 of the f32 values (cartesian_netcdf3.rs:119-120)
-    double inv_x_space, inv_y_space;
+    // per-cell records for the fast path: cell (x1,y1), x1 < nx-1, y1 < ny-1, two float4 each:
+    //   {z_sw, z_nw, z_ne, z_se} (depth as f32)  and  {dhdx, dhdy, 0, 0} (f32 of the f64 quotient)
+    const float4 *cell;
+    // coordinates exactly affine in f32 (x[i] == fmaf(i, dxf, x[0]) for every i, same for y):
+    // corner coordinates and the change-of-basis coefficients become launch constants
+    int32_t uniform;
+    float dxf, dyf, c01, c10;
 };
 
 struct CurrentDev {
     int32_t kind;
     int32_t nx, ny;
-    const double *x, *y, *u, *v;
+    const double *x, *y, *u, *v;   // GRID, f64 nodes                                (strict path)
     double u0, v0;
     // derived at upload (GRID)
     double xd0, yd0;           // x[0], y[0]
     double sx, sy;             // |x[1]-x[0]|, |y[1]-y[0]|          (cartesian_current.rs:244)
     double inv_sx, inv_sy;     // RN(1/sx), RN(1/sy)
     double x_space, y_space;   // x[1]-x[0] (signed)                (cartesian_current.rs:515-516)
-    double inv_x_space, inv_y_space;
+    // fast path: per cell two float4 {u_sw,u_nw,u_ne,u_se}, {v_sw,v_nw,v_ne,v_se} (as f32) and
+    // two double2 {dudx,dudy}, {dvdx,dvdy} (the f64 finite differences, already divided)
+    const float4  *cell_uv;
+    const double2 *cell_grad;
+    const float *xf, *yf;      // coordinates cast to f32 (cartesian_current.rs:375-376)
+    int32_t uniform;
+    float xf0, yf0, dxf, dyf, c01, c10;
 };
 
 static constexpr double kG = 9.8;            // src/wave_ray_path.rs:23
@@ -55,15 +75,21 @@ static constexpr double kG = 9.8;            // src/wave_ray_path.rs:23
 __device__ __forceinline__ double qnan() { return __longlong_as_double(0x7ff8000000000000LL); }
 __device__ __forceinline__ float  qnanf() { return __int_as_float(0x7fc00000); }
 
-// ---- interpolator::bilinear on an axis-aligned cell -------------------------
+// =============================================================================
+// interpolator::bilinear on an axis-aligned cell
+// =============================================================================
 // points a=(xa,ya,z_sw) b=(xa,yb,z_nw) c=(xb,yb,z_ne) d=(xb,ya,z_se), target (tx,ty).
 // With this corner order bt=(0,dy), dt=(dx,0), so (interpolator.rs:64-75)
-//   det = 0 - dx*dy,  c01 = -(dx/det),  c10 = -(dy/det),  c00 = c11 = 0/det,
-//   X = c00*tt0 + c01*tt1 = RN(c01*tt1),  Y = c10*tt0 + c11*tt1 = RN(c10*tt0)
-// (adding a signed zero is exact).  Returns false for det == 0 (Err).
-__device__ __forceinline__ bool bilinear_cell(float xa, float xb, float ya, float yb,
-                                              float zsw, float znw, float zne, float zse,
-                                              float tx, float ty, float &out)
+//   det = 0*0 - dx*dy,  c00 = 0/det, c01 = -(dx/det), c10 = -(dy/det), c11 = 0/det,
+//   X = c00*tt0 + c01*tt1,  Y = c10*tt0 + c11*tt1.
+// c00*tt0 and c11*tt1 are signed zeros and adding a signed zero is exact, so
+// X = RN(c01*tt1), Y = RN(c10*tt0) (only the sign of an exactly-zero result can
+// differ, which no output can observe).
+
+// strict form: every operation of the reference, branches and all
+__device__ __forceinline__ bool bilinear_cell_strict(float xa, float xb, float ya, float yb,
+                                                     float zsw, float znw, float zne, float zse,
+                                                     float tx, float ty, float &out)
 {
     // :46-50 coincidence with a corner, in the order a, b, c, d
     if (tx == xa && ty == ya) { out = zsw; return true; }
@@ -91,34 +117,85 @@ __device__ __forceinline__ bool bilinear_cell(float xa, float xb, float ya, floa
     return true;
 }
 
+// fast form: the cell's geometry (corner coordinates, c01, c10) is resolved once per
+// lookup and shared by every variable interpolated on that cell.
+struct CellGeom {
+    float X, Y;                // fractional coordinates as the reference computes them
+    bool at_xa, at_xb, at_ya, at_yb;   // target coincident with a corner coordinate
+    bool det_ok;
+};
+
+template <bool UNI>
+__device__ __forceinline__ CellGeom cell_geom(float xa, float xb, float ya, float yb,
+                                              float c01u, float c10u, float tx, float ty)
+{
+    CellGeom g;
+    float c01, c10;
+    if (UNI) {
+        c01 = c01u; c10 = c10u;
+        g.det_ok = true;
+    } else {
+        float dx = __fsub_rn(xb, xa), dy = __fsub_rn(yb, ya);
+        float det = __fsub_rn(0.0f, __fmul_rn(dx, dy));
+        g.det_ok = det != 0.0f;
+        c01 = -__fdiv_rn(dx, det);
+        c10 = -__fdiv_rn(dy, det);
+    }
+    g.X = __fmul_rn(c01, __fsub_rn(ty, ya));
+    g.Y = __fmul_rn(c10, __fsub_rn(tx, xa));
+    g.at_xa = tx == xa; g.at_xb = tx == xb;
+    g.at_ya = ty == ya; g.at_yb = ty == yb;
+    return g;
+}
+
+__device__ __forceinline__ float bilinear_eval(const CellGeom &g, float zsw, float znw, float zne, float zse)
+{
+    float a10 = __fsub_rn(znw, zsw);
+    float a01 = __fsub_rn(zse, zsw);
+    float a11 = __fsub_rn(__fsub_rn(__fsub_rn(zne, zsw), a10), a01);
+    float r = __fadd_rn(zsw, __fmul_rn(a10, g.X));
+    r = __fadd_rn(r, __fmul_rn(a01, g.Y));
+    r = __fadd_rn(r, __fmul_rn(__fmul_rn(a11, g.X), g.Y));
+    // interpolator.rs:46-50, in the order a, b, c, d (later selects take precedence)
+    r = (g.at_xb && g.at_ya) ? zse : r;
+    r = (g.at_xb && g.at_yb) ? zne : r;
+    r = (g.at_xa && g.at_yb) ? znw : r;
+    r = (g.at_xa && g.at_ya) ? zsw : r;
+    return r;
+}
+
 // The cell rule of four_corners (cartesian_netcdf3.rs:344-387, cartesian_current.rs
 // :293-336) for an index already known to be in [0, n-1]: left edge -> (0,1), right
 // edge -> (n-2,n-1), on a grid line -> (i,i+1), else (floor,ceil).  All four cases
 // are i1 = min(floor(index), n-2), i2 = i1+1 (n >= 2 is enforced at upload).
+// Out-of-range / NaN indices are clamped so the loads stay in bounds; the caller
+// discards the result.
 __device__ __forceinline__ int cell_of(float index, int n)
 {
-    int i = __float2int_rd(index);
-    return i < n - 2 ? i : n - 2;
+    int i = __float2int_rd(index);           // NaN -> 0, saturating
+    return max(min(i, n - 2), 0);
 }
 __device__ __forceinline__ int cell_of(double index, int n)
 {
     int i = __double2int_rd(index);
-    return i < n - 2 ? i : n - 2;
+    return max(min(i, n - 2), 0);
 }
 
-// ---- BathymetryData::depth_and_gradient -------------------------------------
+// =============================================================================
+// BathymetryData::depth_and_gradient
+// =============================================================================
 // Returns false for Err (the whole RHS then becomes NaN, wave_ray_path.rs:222-228).
-template <int BK, int MATH>
-__device__ __forceinline__ bool bathy_eval(const BathyDev &b, float x, float y,
-                                           float &h, float &gx, float &gy)
+
+__device__ __forceinline__ bool bathy_analytic(int kind, const BathyDev &b, float x, float y,
+                                               float &h, float &gx, float &gy)
 {
-    if (BK == MR_BATHY_CONSTANT) {            // constant_depth.rs:39-45
+    if (kind == MR_BATHY_CONSTANT) {          // constant_depth.rs:39-45
         bool bad = isnan(x) || isnan(y);
         h = bad ? qnanf() : b.h0;
         gx = gy = bad ? qnanf() : 0.0f;
         return true;
     }
-    if (BK == MR_BATHY_SLOPE) {               // constant_slope.rs:67-76
+    if (kind == MR_BATHY_SLOPE) {             // constant_slope.rs:67-76
         bool bad = isnan(x) || isnan(y);
         float s = __fadd_rn(b.h0, __fmul_rn(b.dhdx, __fsub_rn(x, b.x0)));
         s = __fadd_rn(s, __fmul_rn(b.dhdy, __fsub_rn(y, b.y0)));
@@ -127,15 +204,19 @@ __device__ __forceinline__ bool bathy_eval(const BathyDev &b, float x, float y,
         gy = bad ? qnanf() : b.dhdy;
         return true;
     }
-    if (BK == MR_BATHY_ARRAY) {               // array_depth.rs:27-35 (`as usize` saturates)
-        unsigned long long xi = __float2ull_rz(x), yi = __float2ull_rz(y);   // NaN -> 0, negative -> 0, huge -> max
-        unsigned long long len = (unsigned long long)b.nx;
-        bool oob = xi >= len || yi >= len;
-        h = oob ? qnanf() : __ldg(b.array + (oob ? 0 : xi * (unsigned long long)b.ny + yi));
-        gx = gy = oob ? qnanf() : 0.0f;
-        return true;
-    }
-    // GRID: cartesian_netcdf3.rs:98-135
+    // ARRAY: array_depth.rs:27-35 (`as usize` saturates)
+    unsigned long long xi = __float2ull_rz(x), yi = __float2ull_rz(y);   // NaN -> 0, negative -> 0, huge -> max
+    unsigned long long len = (unsigned long long)b.nx;
+    bool oob = xi >= len || yi >= len;
+    h = oob ? qnanf() : __ldg(b.array + (oob ? 0 : xi * (unsigned long long)b.ny + yi));
+    gx = gy = oob ? qnanf() : 0.0f;
+    return true;
+}
+
+// GRID, strict: cartesian_netcdf3.rs:98-135 on the f64 node grid
+__device__ __forceinline__ bool bathy_grid_strict(const BathyDev &b, float x, float y,
+                                                  float &h, float &gx, float &gy)
+{
     if (isnan(x) || isnan(y)) { h = gx = gy = qnanf(); return true; }          // :101-103
     float ix = __fdiv_rn(__fsub_rn(x, b.xf0), b.sx);                          // :289
     float iy = __fdiv_rn(__fsub_rn(y, b.yf0), b.sy);
@@ -150,45 +231,52 @@ __device__ __forceinline__ bool bathy_eval(const BathyDev &b, float x, float y,
     double dnw = __ldg(row1), dne = __ldg(row1 + 1);
     float xa = __ldg(b.x + x1), xb = __ldg(b.x + x1 + 1);
     float ya = __ldg(b.y + y1), yb = __ldg(b.y + y1 + 1);
-    if (!bilinear_cell(xa, xb, ya, yb, (float)dsw, (float)dnw, (float)dne, (float)dse, x, y, h))
+    if (!bilinear_cell_strict(xa, xb, ya, yb, (float)dsw, (float)dnw, (float)dne, (float)dse, x, y, h))
         return false;
-    if (MATH == MR_MATH_STRICT) {             // :126-134
-        gx = (float)__ddiv_rn(__dsub_rn(dse, dsw), b.x_space);
-        gy = (float)__ddiv_rn(__dsub_rn(dnw, dsw), b.y_space);
-    } else {
-        gx = (float)((dse - dsw) * b.inv_x_space);
-        gy = (float)((dnw - dsw) * b.inv_y_space);
-    }
+    gx = (float)__ddiv_rn(__dsub_rn(dse, dsw), b.x_space);                    // :126-134
+    gy = (float)__ddiv_rn(__dsub_rn(dnw, dsw), b.y_space);
     return true;
 }
 
-// ---- CurrentData::current_and_gradient --------------------------------------
+// GRID, fast: same values from the per-cell records; branch-free
+template <bool UNI>
+__device__ __forceinline__ bool bathy_grid_fast(const BathyDev &b, float x, float y,
+                                                float &h, float &gx, float &gy)
+{
+    const bool isn = isnan(x) || isnan(y);                                    // :101-103 -> Ok(NaN..)
+    float ix = __fdiv_rn(__fsub_rn(x, b.xf0), b.sx);                          // :289 (IEEE f32 divide)
+    float iy = __fdiv_rn(__fsub_rn(y, b.yf0), b.sy);
+    const bool inside = ix >= 0.0f && ix <= (float)(b.nx - 1) && iy >= 0.0f && iy <= (float)(b.ny - 1);
+    const int x1 = cell_of(ix, b.nx), y1 = cell_of(iy, b.ny);
+    const float4 *rec = b.cell + 2 * ((size_t)(b.nx - 1) * y1 + x1);
+    const float4 z = __ldg(rec);
+    const float4 g = __ldg(rec + 1);
+    float xa, xb, ya, yb;
+    if (UNI) {
+        xa = __fmaf_rn((float)x1, b.dxf, b.xf0); xb = __fadd_rn(xa, b.dxf);
+        ya = __fmaf_rn((float)y1, b.dyf, b.yf0); yb = __fadd_rn(ya, b.dyf);
+    } else {
+        xa = __ldg(b.x + x1); xb = __ldg(b.x + x1 + 1);
+        ya = __ldg(b.y + y1); yb = __ldg(b.y + y1 + 1);
+    }
+    const CellGeom cg = cell_geom<UNI>(xa, xb, ya, yb, b.c01, b.c10, x, y);
+    const float r = bilinear_eval(cg, z.x, z.y, z.z, z.w);
+    h  = isn ? qnanf() : r;
+    gx = isn ? qnanf() : g.x;
+    gy = isn ? qnanf() : g.y;
+    return isn || (inside && cg.det_ok);
+}
+
+// =============================================================================
+// CurrentData::current_and_gradient
+// =============================================================================
 struct CurrentVal { double u, v, dudx, dudy, dvdx, dvdy; };
 
-template <int CK, int MATH>
-__device__ __forceinline__ bool current_eval(const CurrentDev &c, double x, double y, CurrentVal &o)
+// GRID, strict: cartesian_current.rs:487-542 on the f64 node grids
+__device__ __forceinline__ bool current_grid_strict(const CurrentDev &c, double x, double y, CurrentVal &o)
 {
-    if (CK == MR_CURRENT_CONSTANT) {          // constant_current.rs:69-77
-        o.u = c.u0; o.v = c.v0;
-        o.dudx = o.dudy = o.dvdx = o.dvdy = 0.0;
-        return true;
-    }
-    // GRID: cartesian_current.rs:487-542.  f64 fractional index (:246).
-    double tx = x - c.xd0, ty = y - c.yd0;
-    double ix, iy;
-    if (MATH == MR_MATH_STRICT) {
-        ix = __ddiv_rn(tx, c.sx);
-        iy = __ddiv_rn(ty, c.sy);
-    } else {
-        // quotient by the loop-invariant spacing: q0 = t*RN(1/s), one residual
-        // correction (exact whenever t/s is representable, e.g. on a grid line)
-        double qx = tx * c.inv_sx, qy = ty * c.inv_sy;
-        ix = fma(fma(-qx, c.sx, tx), c.inv_sx, qx);
-        iy = fma(fma(-qy, c.sy, ty), c.inv_sy, qy);
-        // inf - keeps inf (fma(-inf, s, inf) is NaN): restore the reference's inf -> OOB
-        if (isinf(tx)) ix = tx;
-        if (isinf(ty)) iy = ty;
-    }
+    double ix = __ddiv_rn(x - c.xd0, c.sx);                               // :246
+    double iy = __ddiv_rn(y - c.yd0, c.sy);
     // :248  a NaN index passes this test in the reference; floor/ceil of NaN cast to 0
     // make x1 == x2, det == 0, Err (interpolator.rs:65).  Both ways: Err.
     if (!(ix >= 0.0 && ix <= (double)(c.nx - 1))) return false;
@@ -203,26 +291,59 @@ __device__ __forceinline__ bool current_eval(const CurrentDev &c, double x, doub
     float ya = (float)__ldg(c.y + y1), yb = (float)__ldg(c.y + y1 + 1);
     float xf = (float)x, yf = (float)y;                                   // :500
     float uf, vf;
-    if (!bilinear_cell(xa, xb, ya, yb, (float)usw, (float)unw, (float)une, (float)use_, xf, yf, uf)) return false;
-    if (!bilinear_cell(xa, xb, ya, yb, (float)vsw, (float)vnw, (float)vne, (float)vse, xf, yf, vf)) return false;
+    if (!bilinear_cell_strict(xa, xb, ya, yb, (float)usw, (float)unw, (float)une, (float)use_, xf, yf, uf)) return false;
+    if (!bilinear_cell_strict(xa, xb, ya, yb, (float)vsw, (float)vnw, (float)vne, (float)vse, xf, yf, vf)) return false;
     o.u = (double)uf; o.v = (double)vf;
-    if (MATH == MR_MATH_STRICT) {             // :522-536
-        o.dudx = __ddiv_rn(__dsub_rn(use_, usw), c.x_space);
-        o.dudy = __ddiv_rn(__dsub_rn(unw, usw), c.y_space);
-        o.dvdx = __ddiv_rn(__dsub_rn(vse, vsw), c.x_space);
-        o.dvdy = __ddiv_rn(__dsub_rn(vnw, vsw), c.y_space);
-    } else {
-        o.dudx = (use_ - usw) * c.inv_x_space;
-        o.dudy = (unw - usw) * c.inv_y_space;
-        o.dvdx = (vse - vsw) * c.inv_x_space;
-        o.dvdy = (vnw - vsw) * c.inv_y_space;
-    }
+    o.dudx = __ddiv_rn(__dsub_rn(use_, usw), c.x_space);                  // :522-536
+    o.dudy = __ddiv_rn(__dsub_rn(unw, usw), c.y_space);
+    o.dvdx = __ddiv_rn(__dsub_rn(vse, vsw), c.x_space);
+    o.dvdy = __ddiv_rn(__dsub_rn(vnw, vsw), c.y_space);
     return true;
 }
 
-// ---- the f64 stage, reference expression tree (MR_MATH_STRICT) ---------------
+// GRID, fast.  (xf, yf) = (x as f32, y as f32), shared with the bathymetry lookup.
+template <bool UNI>
+__device__ __forceinline__ bool current_grid_fast(const CurrentDev &c, double x, double y,
+                                                  float xf, float yf, CurrentVal &o)
+{
+    // f64 fractional index (:246).  The spacing is a launch constant: q0 = t*RN(1/s)
+    // and one exact-residual correction give the quotient, exactly whenever t/s is
+    // representable (a ray sitting on a grid line), within one ulp otherwise.
+    const double tx = x - c.xd0, ty = y - c.yd0;
+    const double qx = tx * c.inv_sx, qy = ty * c.inv_sy;
+    double ix = fma(fma(-qx, c.sx, tx), c.inv_sx, qx);
+    double iy = fma(fma(-qy, c.sy, ty), c.inv_sy, qy);
+    // an infinite position must stay out of bounds (fma(-inf, s, inf) is NaN): a NaN
+    // index fails the test below just as the infinite one does
+    const bool inside = ix >= 0.0 && ix <= (double)(c.nx - 1) && iy >= 0.0 && iy <= (double)(c.ny - 1);
+    const int x1 = cell_of(ix, c.nx), y1 = cell_of(iy, c.ny);
+    const size_t cell = (size_t)(c.nx - 1) * y1 + x1;
+    const float4 U = __ldg(c.cell_uv + 2 * cell);
+    const float4 V = __ldg(c.cell_uv + 2 * cell + 1);
+    const double2 gu = __ldg(c.cell_grad + 2 * cell);
+    const double2 gv = __ldg(c.cell_grad + 2 * cell + 1);
+    float xa, xb, ya, yb;
+    if (UNI) {
+        xa = __fmaf_rn((float)x1, c.dxf, c.xf0); xb = __fadd_rn(xa, c.dxf);
+        ya = __fmaf_rn((float)y1, c.dyf, c.yf0); yb = __fadd_rn(ya, c.dyf);
+    } else {
+        xa = __ldg(c.xf + x1); xb = __ldg(c.xf + x1 + 1);
+        ya = __ldg(c.yf + y1); yb = __ldg(c.yf + y1 + 1);
+    }
+    const CellGeom cg = cell_geom<UNI>(xa, xb, ya, yb, c.c01, c.c10, xf, yf);
+    o.u = (double)bilinear_eval(cg, U.x, U.y, U.z, U.w);
+    o.v = (double)bilinear_eval(cg, V.x, V.y, V.z, V.w);
+    o.dudx = gu.x; o.dudy = gu.y; o.dvdx = gv.x; o.dvdy = gv.y;
+    return inside && cg.det_ok;
+}
+
+// =============================================================================
+// the f64 stage
+// =============================================================================
+
+// ---- reference expression tree (MR_MATH_STRICT) --------------------------------
 // wave_ray_path.rs:132-147 with group_velocity :177-188 and dkdt_bathy :207-216.
-// This translation unit is compiled with -fmad=false; the explicit _rn
+// The strict translation unit is compiled with -fmad=false; the explicit _rn
 // intrinsics make the intent visible as well.
 __device__ __forceinline__ void rhs_f64_strict(double kx, double ky, double h, double dhdx, double dhdy,
                                                const CurrentVal &cv, double out[4])
@@ -258,60 +379,134 @@ __device__ __forceinline__ void rhs_f64_strict(double kx, double ky, double h, d
     out[3] = __dsub_rn(__dsub_rn(by, __dmul_rn(kx, cv.dudy)), __dmul_rn(ky, cv.dvdy));   // :147
 }
 
-// ---- the f64 stage, restructured (MR_MATH_FAST) ------------------------------
-// Same functions of (k, h), evaluated from ONE exponential:
+// ---- lean f64 primitives (MR_MATH_FAST) ------------------------------------------
+// For normal, positive, finite arguments (what the path produces when `ok`); other
+// inputs give NaN/garbage that the caller replaces.
+
+// sqrt(x) and 1/sqrt(x) together: MUFU.RSQ64H seed (~2^-23) + two coupled
+// Goldschmidt steps -> both within ~1 ulp.
+__device__ __forceinline__ void sqrt_rsqrt(double x, double &s, double &rs)
+{
+    double y0;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
+    double g = x * y0, hh = 0.5 * y0;
+    double r = fma(-g, hh, 0.5);
+    g = fma(g, r, g); hh = fma(hh, r, hh);
+    r = fma(-g, hh, 0.5);
+    g = fma(g, r, g); hh = fma(hh, r, hh);
+    s = g; rs = hh + hh;
+}
+
+// 1/x: MUFU.RCP64H seed + two Newton steps
+__device__ __forceinline__ double recip(double x)
+{
+    double r0;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(x));
+    double e = fma(-x, r0, 1.0);
+    r0 = fma(r0, e, r0);
+    e = fma(-x, r0, 1.0);
+    return fma(r0, e, r0);
+}
+
+// E = exp(z) and em = expm1(z) for z in [-700, 0] (z is clamped by the caller).
+// z = n ln2 + r, |r| <= ln2/2;  expm1(r) = r + r^2 P(r) (Taylor through r^13, remainder
+// < 2e-17 relative);  E = 2^n (1 + p),  em = 2^n p + (2^n - 1)  (2^n - 1 is exact).
+__device__ __forceinline__ void exp_expm1_neg(double z, double &E, double &em)
+{
+    const double L2E = 1.4426950408889634074, MAGIC = 6755399441055744.0;   // 1.5 * 2^52
+    const double LN2_HI = 6.93147180369123816490e-01, LN2_LO = 1.90821492927058770002e-10;
+    double t = fma(z, L2E, MAGIC);                 // low word of t = rint(z*log2e) as int32
+    int n = __double2loint(t);
+    double nd = t - MAGIC;
+    double r = fma(-nd, LN2_HI, z);
+    r = fma(-nd, LN2_LO, r);
+    double p = 1.6059043836821613e-10;             // 1/13!
+    p = fma(p, r, 2.08767569878681e-09);           // 1/12!
+    p = fma(p, r, 2.505210838544172e-08);          // 1/11!
+    p = fma(p, r, 2.755731922398589e-07);          // 1/10!
+    p = fma(p, r, 2.7557319223985893e-06);         // 1/9!
+    p = fma(p, r, 2.48015873015873e-05);           // 1/8!
+    p = fma(p, r, 1.984126984126984e-04);          // 1/7!
+    p = fma(p, r, 1.388888888888889e-03);          // 1/6!
+    p = fma(p, r, 8.333333333333333e-03);          // 1/5!
+    p = fma(p, r, 4.1666666666666664e-02);         // 1/4!
+    p = fma(p, r, 1.6666666666666666e-01);         // 1/3!
+    p = fma(p, r, 0.5);                            // 1/2!
+    p = fma(r * r, p, r);                          // expm1(r)
+    double s = __hiloint2double((n + 1023) << 20, 0);   // 2^n, n in [-1010, 0]
+    E = fma(s, p, s);
+    em = fma(s, p, s - 1.0);
+}
+
+// ---- restructured f64 stage (MR_MATH_FAST) ------------------------------------------
+// Same functions of (k, h) as the reference, evaluated from ONE exponential:
 //   E = exp(-2kh), m = 1-E = -expm1(-2kh), w = 1+E
 //   tanh kh = m/w,  1/cosh^2 kh = 4E/w^2,  1/(sinh kh cosh kh) = 4E/(m w)
 // and cos(theta) = kx/k, sin(theta) = ky/k instead of atan2 + sincos.
 // Special values follow the reference: h <= 0, h NaN, k == 0, k NaN -> four NaN;
-// large kh: E underflows to 0 -> tanh = 1, second cg term 0, bathymetric term -0
-// (the reference gets the same from cosh^2 -> inf and sinh -> inf).
+// large kh: E -> 0, tanh = 1, second cg term 0, bathymetric term -0 (the reference
+// gets the same from cosh^2 -> inf and sinh -> inf).
 __device__ __forceinline__ void rhs_f64_fast(double kx, double ky, double h, double dhdx, double dhdy,
-                                             const CurrentVal &cv, double out[4])
+                                             const CurrentVal &cv, bool fields_ok, double out[4])
 {
-    double k2 = fma(kx, kx, ky * ky);
-    bool ok = (h > 0.0) && (k2 > 0.0);        // false for NaN h / NaN k as well
-    double rk = rsqrt(k2);
-    double k = k2 * rk;
-    double cs = kx * rk, sn = ky * rk;
-    double kh = k * h;
-    double em = expm1(-2.0 * kh);             // E - 1, in [-1, 0)
-    double E = 1.0 + em;
-    double m = -em, w = 2.0 + em;
-    double r = 1.0 / (m * w);
-    double invw = m * r;
-    double T = m * invw;                      // tanh(kh)
-    double E4 = 4.0 * E;
-    double sech2 = E4 * invw * invw;
-    double csch_sech = E4 * r;
-    double q = (k * kG) * T;
-    double rq = rsqrt(q);
-    double cg = (kG * 0.5) * ((T + kh * sech2) * rq);
-    double Bc = (-0.5 * k) * csch_sech * (q * rq);
-    double nan = qnan();
-    out[0] = ok ? fma(cg, cs, cv.u) : nan;
-    out[1] = ok ? fma(cg, sn, cv.v) : nan;
+    const double k2 = fma(kx, kx, ky * ky);
+    const bool ok = fields_ok && (h > 0.0) && (k2 > 0.0);        // false for NaN h / NaN k as well
+    // h = +inf: the reference's cg is inf/inf = NaN while its bathymetric term is -0
+    const bool cg_ok = ok && (h < __longlong_as_double(0x7ff0000000000000LL));
+    double k, rk;
+    sqrt_rsqrt(k2, k, rk);
+    const double cs = kx * rk, sn = ky * rk;
+    const double kh = k * h;
+    double E, em;
+    exp_expm1_neg(fmax(-2.0 * kh, -700.0), E, em);
+    const double m = -em, w = 2.0 + em;
+    const double r = recip(m * w);
+    const double invw = m * r;
+    const double T = m * invw;                // tanh(kh)
+    const double E4 = 4.0 * E;
+    const double sech2 = (E4 * invw) * invw;
+    const double csch_sech = E4 * r;
+    const double q = (k * kG) * T;
+    double sq, rq;
+    sqrt_rsqrt(q, sq, rq);
+    const double cg = (kG * 0.5) * (fma(kh, sech2, T) * rq);
+    const double Bc = ((-0.5 * k) * csch_sech) * sq;
+    const double nan = qnan();
+    out[0] = cg_ok ? fma(cg, cs, cv.u) : nan;
+    out[1] = cg_ok ? fma(cg, sn, cv.v) : nan;
     out[2] = ok ? fma(-ky, cv.dvdx, fma(-kx, cv.dudx, Bc * dhdx)) : nan;
     out[3] = ok ? fma(-ky, cv.dvdy, fma(-kx, cv.dudy, Bc * dhdy)) : nan;
 }
 
-// ---- System::system (wave_ray_path.rs:220-234): Err -> four NaN ---------------
-template <int BK, int CK, int MATH>
+// =============================================================================
+// System::system (wave_ray_path.rs:220-234): Err -> four NaN
+// =============================================================================
+template <int BK, int CK, int MATH, bool UNI>
 __device__ __forceinline__ void rhs(const BathyDev &b, const CurrentDev &c,
                                     double x, double y, double kx, double ky, double out[4])
 {
+    const float xf = (float)x, yf = (float)y;                                  // :122
     float h32, gx32, gy32;
-    bool ok = bathy_eval<BK, MATH>(b, (float)x, (float)y, h32, gx32, gy32);   // :120-122
     CurrentVal cv;
-    if (ok) ok = current_eval<CK, MATH>(c, x, y, cv);                          // :129
-    if (!ok) {
-        out[0] = out[1] = out[2] = out[3] = qnan();
-        return;
-    }
-    if (MATH == MR_MATH_STRICT)
+    if (MATH == MR_MATH_STRICT) {
+        bool ok = (BK == MR_BATHY_GRID) ? bathy_grid_strict(b, xf, yf, h32, gx32, gy32)
+                                        : bathy_analytic(BK, b, xf, yf, h32, gx32, gy32);   // :120-122
+        if (ok) {
+            if (CK == MR_CURRENT_GRID) ok = current_grid_strict(c, x, y, cv);              // :129
+            else { cv.u = c.u0; cv.v = c.v0; cv.dudx = cv.dudy = cv.dvdx = cv.dvdy = 0.0; }
+        }
+        if (!ok) {
+            out[0] = out[1] = out[2] = out[3] = qnan();
+            return;
+        }
         rhs_f64_strict(kx, ky, (double)h32, (double)gx32, (double)gy32, cv, out);
-    else
-        rhs_f64_fast(kx, ky, (double)h32, (double)gx32, (double)gy32, cv, out);
+    } else {
+        bool ok = (BK == MR_BATHY_GRID) ? bathy_grid_fast<UNI>(b, xf, yf, h32, gx32, gy32)
+                                        : bathy_analytic(BK, b, xf, yf, h32, gx32, gy32);
+        if (CK == MR_CURRENT_GRID) ok = current_grid_fast<UNI>(c, x, y, xf, yf, cv) && ok;
+        else { cv.u = c.u0; cv.v = c.v0; cv.dudx = cv.dudy = cv.dvdx = cv.dvdy = 0.0; }   // constant_current.rs:69-77
+        rhs_f64_fast(kx, ky, (double)h32, (double)gx32, (double)gy32, cv, ok, out);
+    }
 }
 
 }  // namespace mr

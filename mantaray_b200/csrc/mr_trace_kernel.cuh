@@ -17,6 +17,10 @@
 // reaches are NaN too (python/mantaray/core.py:115-119), so a stopped lane just
 // keeps storing its NaN state; when a whole warp has stopped it leaves the RK4
 // loop and only fills.
+//
+// The four stages run as ONE loop body (stage offset a_s in {0, dt/2, dt/2, dt},
+// weight w_s in {1, 2, 2, 1}; multiplying by 1 or 2 is exact, so the accumulation
+// order is the reference's) to keep the kernel inside the instruction cache.
 #pragma once
 #include "mr_device.cuh"
 
@@ -47,8 +51,8 @@ __device__ __forceinline__ bool all_nan4(const double y[4])
     return isnan(y[0]) && isnan(y[1]) && isnan(y[2]) && isnan(y[3]);
 }
 
-template <int BK, int CK, int MATH>
-__global__ void __launch_bounds__(kBlock)
+template <int BK, int CK, int MATH, bool UNI>
+__global__ void __launch_bounds__(kBlock, (MATH == MR_MATH_FAST) ? 5 : 1)
 trace_kernel(const __grid_constant__ TraceArgs a)
 {
     const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
@@ -82,33 +86,29 @@ trace_kernel(const __grid_constant__ TraceArgs a)
     for (; s <= a.nsteps; ++s) {
         if (!__any_sync(0xffffffffu, alive)) break;
         if (alive) {
-            double k[4], acc[4], yt[4];
-            rhs<BK, CK, MATH>(a.b, a.c, y[0], y[1], y[2], y[3], k);
-            const bool k0_nan = all_nan4(k);
+            double k[4] = {0.0, 0.0, 0.0, 0.0};
+            double acc[4] = {-0.0, -0.0, -0.0, -0.0};     // -0 + k0 == k0 for every k0
+            bool k0_nan = false;
+#pragma unroll 1
+            for (int st = 0; st < 4; ++st) {
+                const double as = (st == 0) ? 0.0 : (st == 3 ? dt : half);
+                const double ws = (st == 1 || st == 2) ? 2.0 : 1.0;
+                double yt[4];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                acc[c] = k[c];
-                yt[c] = (MATH == MR_MATH_STRICT) ? __dadd_rn(y[c], __dmul_rn(k[c], half)) : fma(k[c], half, y[c]);
-            }
-            rhs<BK, CK, MATH>(a.b, a.c, yt[0], yt[1], yt[2], yt[3], k);
+                for (int c = 0; c < 4; ++c) {
+                    const double adv = (MATH == MR_MATH_STRICT) ? __dadd_rn(y[c], __dmul_rn(k[c], as)) : fma(k[c], as, y[c]);
+                    yt[c] = (st == 0) ? y[c] : adv;
+                }
+                rhs<BK, CK, MATH, UNI>(a.b, a.c, yt[0], yt[1], yt[2], yt[3], k);
+                if (st == 0) k0_nan = all_nan4(k);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                acc[c] = __dadd_rn(acc[c], __dmul_rn(k[c], 2.0));      // (k0 + k1*2): *2 is exact
-                yt[c] = (MATH == MR_MATH_STRICT) ? __dadd_rn(y[c], __dmul_rn(k[c], half)) : fma(k[c], half, y[c]);
+                for (int c = 0; c < 4; ++c)
+                    acc[c] = (MATH == MR_MATH_STRICT) ? __dadd_rn(acc[c], __dmul_rn(k[c], ws)) : fma(k[c], ws, acc[c]);
             }
-            rhs<BK, CK, MATH>(a.b, a.c, yt[0], yt[1], yt[2], yt[3], k);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                acc[c] = __dadd_rn(acc[c], __dmul_rn(k[c], 2.0));
-                yt[c] = (MATH == MR_MATH_STRICT) ? __dadd_rn(y[c], __dmul_rn(k[c], dt)) : fma(k[c], dt, y[c]);
-            }
-            rhs<BK, CK, MATH>(a.b, a.c, yt[0], yt[1], yt[2], yt[3], k);
             double yn[4];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                acc[c] = __dadd_rn(acc[c], k[c]);
+            for (int c = 0; c < 4; ++c)
                 yn[c] = (MATH == MR_MATH_STRICT) ? __dadd_rn(y[c], __dmul_rn(acc[c], sixth)) : fma(acc[c], sixth, y[c]);
-            }
             rows = (int32_t)(s + 1);
             if (clean) {
                 if (any_nan4(yn)) {
@@ -151,15 +151,23 @@ trace_kernel(const __grid_constant__ TraceArgs a)
     }
 }
 
-// One instantiation per (bathymetry kind, current kind); the kinds are uniform
-// over a launch, so the dispatch is a host-side switch.
+// One instantiation per (bathymetry kind, current kind[, uniform grids]); the kinds are
+// uniform over a launch, so the dispatch is a host-side switch.
 template <int MATH>
 static cudaError_t launch_trace_math(const TraceArgs &a, cudaStream_t stream)
 {
     if (a.n <= 0) return cudaSuccess;
     const unsigned grid = (unsigned)((a.n + kBlock - 1) / kBlock);
-#define MR_CASE(BKV, CKV) \
-    if (a.b.kind == BKV && a.c.kind == CKV) { trace_kernel<BKV, CKV, MATH><<<grid, kBlock, 0, stream>>>(a); return cudaGetLastError(); }
+    // the fast path's affine-coordinate specialisation needs every gridded field to qualify
+    const bool uni = MATH == MR_MATH_FAST &&
+                     (a.b.kind != MR_BATHY_GRID || a.b.uniform) && (a.c.kind != MR_CURRENT_GRID || a.c.uniform) &&
+                     (a.b.kind == MR_BATHY_GRID || a.c.kind == MR_CURRENT_GRID);
+#define MR_CASE(BKV, CKV)                                                                                      \
+    if (a.b.kind == BKV && a.c.kind == CKV) {                                                                  \
+        if (uni) trace_kernel<BKV, CKV, MATH, (MATH == MR_MATH_FAST)><<<grid, kBlock, 0, stream>>>(a);         \
+        else     trace_kernel<BKV, CKV, MATH, false><<<grid, kBlock, 0, stream>>>(a);                          \
+        return cudaGetLastError();                                                                             \
+    }
     MR_CASE(MR_BATHY_CONSTANT, MR_CURRENT_CONSTANT)
     MR_CASE(MR_BATHY_CONSTANT, MR_CURRENT_GRID)
     MR_CASE(MR_BATHY_SLOPE,    MR_CURRENT_CONSTANT)

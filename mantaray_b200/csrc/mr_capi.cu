@@ -204,6 +204,18 @@ static bool basis_coeffs(float dx, float dy, float *c01, float *c10)
     return std::isfinite(*c01) && std::isfinite(*c10);
 }
 
+// RN(1/s) for fdiv_const; refused for subnormal / huge s and for the all-ones significand
+// that Markstein's theorem excludes
+static bool recip_ok(float s, float *r)
+{
+    uint32_t bits;
+    std::memcpy(&bits, &s, 4);
+    if (!(s > 1e-30f) || !(s < 1e30f) || (bits & 0x7fffffu) == 0x7fffffu) return false;
+    volatile float q = 1.0f / s;
+    *r = q;
+    return true;
+}
+
 template <typename T>
 static int device_alloc(DeviceFields &d, size_t count, T **out)
 {
@@ -237,7 +249,7 @@ static int upload_fields(DeviceFields &d, const mr_bathymetry_desc *b, const mr_
         MR_CUDA(cudaGetLastError());
         B.cell = cell;
         B.uniform = affine_f32(b->x, b->nx, &B.dxf) && affine_f32(b->y, b->ny, &B.dyf) &&
-                    basis_coeffs(B.dxf, B.dyf, &B.c01, &B.c10);
+                    basis_coeffs(B.dxf, B.dyf, &B.c01, &B.c10) && recip_ok(B.sx, &B.rsx) && recip_ok(B.sy, &B.rsy);
     } else if (b->kind == MR_BATHY_ARRAY) {
         int rc;
         if ((rc = upload(d, b->array, (size_t)b->nx * b->ny, &B.array))) return rc;

@@ -41,6 +41,7 @@ struct BathyDev {
     // derived at upload (GRID)
     float  xf0, yf0;           // x[0], y[0]
     float  sx, sy;             // |x[1]-x[0]|, |y[1]-y[0]| in f32   (cartesian_netcdf3.rs:287)
+    float  rsx, rsy;           // RN(1/sx), RN(1/sy); 0 when the exact-division shortcut does not apply
     double x_space, y_space;   // x[1]-x[0] in f64 of the f32 values (cartesian_netcdf3.rs:119-120)
     // per-cell records for the fast path: cell (x1,y1), x1 < nx-1, y1 < ny-1, two float4 each:
     //   {z_sw, z_nw, z_ne, z_se} (depth as f32)  and  {dhdx, dhdy, 0, 0} (f32 of the f64 quotient)
@@ -71,6 +72,17 @@ struct CurrentDev {
 };
 
 static constexpr double kG = 9.8;            // src/wave_ray_path.rs:23
+
+// Taylor coefficients 1/13! .. 1/2! of expm1 (see exp_expm1_neg).  In constant memory so
+// that each DFMA reads its coefficient as a c[bank][offset] operand instead of the
+// compiler materialising 64-bit immediates with two moves per use.
+static __constant__ double kExpm1C[12] = {
+    1.6059043836821613e-10, 2.08767569878681e-09, 2.505210838544172e-08, 2.755731922398589e-07,
+    2.7557319223985893e-06, 2.48015873015873e-05, 1.984126984126984e-04, 1.388888888888889e-03,
+    8.333333333333333e-03, 4.1666666666666664e-02, 1.6666666666666666e-01, 0.5};
+// {log2(e), 1.5*2^52, ln2_hi, ln2_lo}
+static __constant__ double kExpRed[4] = {1.4426950408889634074, 6755399441055744.0,
+                                         6.93147180369123816490e-01, 1.90821492927058770002e-10};
 
 __device__ __forceinline__ double qnan() { return __longlong_as_double(0x7ff8000000000000LL); }
 __device__ __forceinline__ float  qnanf() { return __int_as_float(0x7fc00000); }
@@ -122,6 +134,7 @@ __device__ __forceinline__ bool bilinear_cell_strict(float xa, float xb, float y
 struct CellGeom {
     float X, Y;                // fractional coordinates as the reference computes them
     bool at_xa, at_xb, at_ya, at_yb;   // target coincident with a corner coordinate
+    bool corner;               // ... with a corner point
     bool det_ok;
 };
 
@@ -145,6 +158,7 @@ __device__ __forceinline__ CellGeom cell_geom(float xa, float xb, float ya, floa
     g.Y = __fmul_rn(c10, __fsub_rn(tx, xa));
     g.at_xa = tx == xa; g.at_xb = tx == xb;
     g.at_ya = ty == ya; g.at_yb = ty == yb;
+    g.corner = (g.at_xa || g.at_xb) && (g.at_ya || g.at_yb);
     return g;
 }
 
@@ -156,12 +170,51 @@ __device__ __forceinline__ float bilinear_eval(const CellGeom &g, float zsw, flo
     float r = __fadd_rn(zsw, __fmul_rn(a10, g.X));
     r = __fadd_rn(r, __fmul_rn(a01, g.Y));
     r = __fadd_rn(r, __fmul_rn(__fmul_rn(a11, g.X), g.Y));
-    // interpolator.rs:46-50, in the order a, b, c, d (later selects take precedence)
-    r = (g.at_xb && g.at_ya) ? zse : r;
-    r = (g.at_xb && g.at_yb) ? zne : r;
-    r = (g.at_xa && g.at_yb) ? znw : r;
-    r = (g.at_xa && g.at_ya) ? zsw : r;
+    // interpolator.rs:46-50: a target coincident with a corner returns that corner's value,
+    // tested in the order a, b, c, d (later selects take precedence).  Rare: one branch.
+    if (g.corner) {
+        r = (g.at_xb && g.at_ya) ? zse : r;
+        r = (g.at_xb && g.at_yb) ? zne : r;
+        r = (g.at_xa && g.at_yb) ? znw : r;
+        r = (g.at_xa && g.at_ya) ? zsw : r;
+    }
     return r;
+}
+
+// IEEE f32 quotient t/s for a launch-constant divisor s with r = RN(1/s) (computed on the
+// host): q0 = RN(t r) is within 2 ulp; one exact-residual step makes it faithful, a second
+// makes it the correctly rounded quotient (Markstein 1990; the host falls back to the true
+// divide if s has an all-ones significand, the theorem's exception).  Verified exhaustively
+// against __fdiv_rn over every float for a set of spacings by tests/test_gpu_division.py.
+// +-inf gives NaN instead of +-inf; both are out of bounds for the caller.
+__device__ __forceinline__ float fdiv_const(float t, float s, float r)
+{
+    float q = __fmul_rn(t, r);
+    q = __fmaf_rn(__fmaf_rn(-q, s, t), r, q);
+    q = __fmaf_rn(__fmaf_rn(-q, s, t), r, q);
+    return q;
+}
+
+// Read-only vector loads as volatile asm: the compiler keeps them where they are written
+// (it otherwise sinks them into the conditional region of their first use, which exposes
+// one full L2 round trip per load instead of one per RHS).
+__device__ __forceinline__ float4 ldg_f4(const float4 *p)
+{
+    float4 v;
+    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float2 ldg_f2(const float2 *p)
+{
+    float2 v;
+    asm volatile("ld.global.nc.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ double2 ldg_d2(const double2 *p)
+{
+    double2 v;
+    asm volatile("ld.global.nc.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
 }
 
 // The cell rule of four_corners (cartesian_netcdf3.rs:344-387, cartesian_current.rs
@@ -238,35 +291,6 @@ __device__ __forceinline__ bool bathy_grid_strict(const BathyDev &b, float x, fl
     return true;
 }
 
-// GRID, fast: same values from the per-cell records; branch-free
-template <bool UNI>
-__device__ __forceinline__ bool bathy_grid_fast(const BathyDev &b, float x, float y,
-                                                float &h, float &gx, float &gy)
-{
-    const bool isn = isnan(x) || isnan(y);                                    // :101-103 -> Ok(NaN..)
-    float ix = __fdiv_rn(__fsub_rn(x, b.xf0), b.sx);                          // :289 (IEEE f32 divide)
-    float iy = __fdiv_rn(__fsub_rn(y, b.yf0), b.sy);
-    const bool inside = ix >= 0.0f && ix <= (float)(b.nx - 1) && iy >= 0.0f && iy <= (float)(b.ny - 1);
-    const int x1 = cell_of(ix, b.nx), y1 = cell_of(iy, b.ny);
-    const float4 *rec = b.cell + 2 * ((size_t)(b.nx - 1) * y1 + x1);
-    const float4 z = __ldg(rec);
-    const float4 g = __ldg(rec + 1);
-    float xa, xb, ya, yb;
-    if (UNI) {
-        xa = __fmaf_rn((float)x1, b.dxf, b.xf0); xb = __fadd_rn(xa, b.dxf);
-        ya = __fmaf_rn((float)y1, b.dyf, b.yf0); yb = __fadd_rn(ya, b.dyf);
-    } else {
-        xa = __ldg(b.x + x1); xb = __ldg(b.x + x1 + 1);
-        ya = __ldg(b.y + y1); yb = __ldg(b.y + y1 + 1);
-    }
-    const CellGeom cg = cell_geom<UNI>(xa, xb, ya, yb, b.c01, b.c10, x, y);
-    const float r = bilinear_eval(cg, z.x, z.y, z.z, z.w);
-    h  = isn ? qnanf() : r;
-    gx = isn ? qnanf() : g.x;
-    gy = isn ? qnanf() : g.y;
-    return isn || (inside && cg.det_ok);
-}
-
 // =============================================================================
 // CurrentData::current_and_gradient
 // =============================================================================
@@ -301,40 +325,45 @@ __device__ __forceinline__ bool current_grid_strict(const CurrentDev &c, double 
     return true;
 }
 
-// GRID, fast.  (xf, yf) = (x as f32, y as f32), shared with the bathymetry lookup.
-template <bool UNI>
-__device__ __forceinline__ bool current_grid_fast(const CurrentDev &c, double x, double y,
-                                                  float xf, float yf, CurrentVal &o)
+// =============================================================================
+// look-ahead prefetch of the per-cell records
+// =============================================================================
+// A ray enters a new cell roughly once per step (dt ~ dd/cg, the reference's own CFL
+// convention), so the first lookup in a cell is a compulsory L1 miss and, with one ray per
+// thread, every warp waits for its slowest lane.  After stage 0 the kernel knows k0; the
+// records under y + 2 dt k0 (the far end of the NEXT step) are requested now and arrive
+// while the remaining three stages run.  Approximate arithmetic is enough here: a wrong
+// guess only costs the miss it failed to hide.
+#ifndef MR_PREFETCH
+#define MR_PREFETCH 0          // 0 off, 1 prefetch.global.L1, 2 prefetch.global.L2
+#endif
+__device__ __forceinline__ void prefetch_line(const void *p)
 {
-    // f64 fractional index (:246).  The spacing is a launch constant: q0 = t*RN(1/s)
-    // and one exact-residual correction give the quotient, exactly whenever t/s is
-    // representable (a ray sitting on a grid line), within one ulp otherwise.
-    const double tx = x - c.xd0, ty = y - c.yd0;
-    const double qx = tx * c.inv_sx, qy = ty * c.inv_sy;
-    double ix = fma(fma(-qx, c.sx, tx), c.inv_sx, qx);
-    double iy = fma(fma(-qy, c.sy, ty), c.inv_sy, qy);
-    // an infinite position must stay out of bounds (fma(-inf, s, inf) is NaN): a NaN
-    // index fails the test below just as the infinite one does
-    const bool inside = ix >= 0.0 && ix <= (double)(c.nx - 1) && iy >= 0.0 && iy <= (double)(c.ny - 1);
-    const int x1 = cell_of(ix, c.nx), y1 = cell_of(iy, c.ny);
-    const size_t cell = (size_t)(c.nx - 1) * y1 + x1;
-    const float4 U = __ldg(c.cell_uv + 2 * cell);
-    const float4 V = __ldg(c.cell_uv + 2 * cell + 1);
-    const double2 gu = __ldg(c.cell_grad + 2 * cell);
-    const double2 gv = __ldg(c.cell_grad + 2 * cell + 1);
-    float xa, xb, ya, yb;
-    if (UNI) {
-        xa = __fmaf_rn((float)x1, c.dxf, c.xf0); xb = __fadd_rn(xa, c.dxf);
-        ya = __fmaf_rn((float)y1, c.dyf, c.yf0); yb = __fadd_rn(ya, c.dyf);
-    } else {
-        xa = __ldg(c.xf + x1); xb = __ldg(c.xf + x1 + 1);
-        ya = __ldg(c.yf + y1); yb = __ldg(c.yf + y1 + 1);
+#if MR_PREFETCH == 1
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#elif MR_PREFETCH == 2
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
+
+template <int BK, int CK>
+__device__ __forceinline__ void prefetch_cells(const BathyDev &b, const CurrentDev &c, double xp, double yp)
+{
+#if MR_PREFETCH
+    const float xf = (float)xp, yf = (float)yp;
+    if (BK == MR_BATHY_GRID) {
+        const int x1 = cell_of(__fdividef(xf - b.xf0, b.sx), b.nx), y1 = cell_of(__fdividef(yf - b.yf0, b.sy), b.ny);
+        prefetch_line(b.cell + 2 * ((size_t)(b.nx - 1) * y1 + x1));
     }
-    const CellGeom cg = cell_geom<UNI>(xa, xb, ya, yb, c.c01, c.c10, xf, yf);
-    o.u = (double)bilinear_eval(cg, U.x, U.y, U.z, U.w);
-    o.v = (double)bilinear_eval(cg, V.x, V.y, V.z, V.w);
-    o.dudx = gu.x; o.dudy = gu.y; o.dvdx = gv.x; o.dvdy = gv.y;
-    return inside && cg.det_ok;
+    if (CK == MR_CURRENT_GRID) {
+        const int x1 = cell_of(__fdividef(xf - c.xf0, (float)c.sx), c.nx), y1 = cell_of(__fdividef(yf - c.yf0, (float)c.sy), c.ny);
+        const size_t cell = (size_t)(c.nx - 1) * y1 + x1;
+        prefetch_line(c.cell_uv + 2 * cell);
+        prefetch_line(c.cell_grad + 2 * cell);
+    }
+#endif
 }
 
 // =============================================================================
@@ -413,25 +442,15 @@ __device__ __forceinline__ double recip(double x)
 // < 2e-17 relative);  E = 2^n (1 + p),  em = 2^n p + (2^n - 1)  (2^n - 1 is exact).
 __device__ __forceinline__ void exp_expm1_neg(double z, double &E, double &em)
 {
-    const double L2E = 1.4426950408889634074, MAGIC = 6755399441055744.0;   // 1.5 * 2^52
-    const double LN2_HI = 6.93147180369123816490e-01, LN2_LO = 1.90821492927058770002e-10;
-    double t = fma(z, L2E, MAGIC);                 // low word of t = rint(z*log2e) as int32
+    const double MAGIC = kExpRed[1];
+    double t = fma(z, kExpRed[0], MAGIC);          // low word of t = rint(z*log2e) as int32
     int n = __double2loint(t);
     double nd = t - MAGIC;
-    double r = fma(-nd, LN2_HI, z);
-    r = fma(-nd, LN2_LO, r);
-    double p = 1.6059043836821613e-10;             // 1/13!
-    p = fma(p, r, 2.08767569878681e-09);           // 1/12!
-    p = fma(p, r, 2.505210838544172e-08);          // 1/11!
-    p = fma(p, r, 2.755731922398589e-07);          // 1/10!
-    p = fma(p, r, 2.7557319223985893e-06);         // 1/9!
-    p = fma(p, r, 2.48015873015873e-05);           // 1/8!
-    p = fma(p, r, 1.984126984126984e-04);          // 1/7!
-    p = fma(p, r, 1.388888888888889e-03);          // 1/6!
-    p = fma(p, r, 8.333333333333333e-03);          // 1/5!
-    p = fma(p, r, 4.1666666666666664e-02);         // 1/4!
-    p = fma(p, r, 1.6666666666666666e-01);         // 1/3!
-    p = fma(p, r, 0.5);                            // 1/2!
+    double r = fma(-nd, kExpRed[2], z);
+    r = fma(-nd, kExpRed[3], r);
+    double p = kExpm1C[0];
+#pragma unroll
+    for (int i = 1; i < 12; ++i) p = fma(p, r, kExpm1C[i]);
     p = fma(r * r, p, r);                          // expm1(r)
     double s = __hiloint2double((n + 1023) << 20, 0);   // 2^n, n in [-1010, 0]
     E = fma(s, p, s);
@@ -446,16 +465,13 @@ __device__ __forceinline__ void exp_expm1_neg(double z, double &E, double &em)
 // Special values follow the reference: h <= 0, h NaN, k == 0, k NaN -> four NaN;
 // large kh: E -> 0, tanh = 1, second cg term 0, bathymetric term -0 (the reference
 // gets the same from cosh^2 -> inf and sinh -> inf).
-__device__ __forceinline__ void rhs_f64_fast(double kx, double ky, double h, double dhdx, double dhdy,
+__device__ __forceinline__ void rhs_f64_fast(double kx, double ky, double k2, double k, double cs, double sn,
+                                             double h, double dhdx, double dhdy,
                                              const CurrentVal &cv, bool fields_ok, double out[4])
 {
-    const double k2 = fma(kx, kx, ky * ky);
     const bool ok = fields_ok && (h > 0.0) && (k2 > 0.0);        // false for NaN h / NaN k as well
     // h = +inf: the reference's cg is inf/inf = NaN while its bathymetric term is -0
     const bool cg_ok = ok && (h < __longlong_as_double(0x7ff0000000000000LL));
-    double k, rk;
-    sqrt_rsqrt(k2, k, rk);
-    const double cs = kx * rk, sn = ky * rk;
     const double kh = k * h;
     double E, em;
     exp_expm1_neg(fmax(-2.0 * kh, -700.0), E, em);
@@ -476,6 +492,113 @@ __device__ __forceinline__ void rhs_f64_fast(double kx, double ky, double h, dou
     out[1] = cg_ok ? fma(cg, sn, cv.v) : nan;
     out[2] = ok ? fma(-ky, cv.dvdx, fma(-kx, cv.dudx, Bc * dhdx)) : nan;
     out[3] = ok ? fma(-ky, cv.dvdy, fma(-kx, cv.dudy, Bc * dhdy)) : nan;
+}
+
+// =============================================================================
+// the fast RHS, in four phases so that every load of an evaluation is in flight
+// before anything waits on one:
+//   1. fractional indices and cell addresses of both fields
+//   2. all record loads
+//   3. the wavenumber-only f64 work (k, 1/k, direction cosines) under the loads
+//   4. f32 bilinears, then the f64 stage
+// =============================================================================
+template <int BK, int CK, bool UNI>
+__device__ __forceinline__ void rhs_fast(const BathyDev &b, const CurrentDev &c,
+                                         double x, double y, double kx, double ky,
+                                         float xf, float yf, double out[4])
+{
+    // ---- phase 1 ---------------------------------------------------------------------
+    bool ok = true;
+    const bool isn = isnan(xf) || isnan(yf);
+    int bx1 = 0, by1 = 0, cx1 = 0, cy1 = 0;
+    const float4 *brec = nullptr;
+    size_t ccell = 0;
+    if (BK == MR_BATHY_GRID) {
+        float ix, iy;                                                          // cartesian_netcdf3.rs:289
+        if (UNI) {
+            ix = fdiv_const(__fsub_rn(xf, b.xf0), b.sx, b.rsx);
+            iy = fdiv_const(__fsub_rn(yf, b.yf0), b.sy, b.rsy);
+        } else {
+            ix = __fdiv_rn(__fsub_rn(xf, b.xf0), b.sx);
+            iy = __fdiv_rn(__fsub_rn(yf, b.yf0), b.sy);
+        }
+        // :291 out of bounds -> Err; :101-103 NaN position -> Ok(NaN, (NaN, NaN))
+        ok = isn || (ix >= 0.0f && ix <= (float)(b.nx - 1) && iy >= 0.0f && iy <= (float)(b.ny - 1));
+        bx1 = cell_of(ix, b.nx); by1 = cell_of(iy, b.ny);
+        brec = b.cell + 2 * ((size_t)(b.nx - 1) * by1 + bx1);
+    }
+    if (CK == MR_CURRENT_GRID) {
+        // f64 fractional index (cartesian_current.rs:246).  The spacing is a launch constant:
+        // q0 = t*RN(1/s) and one exact-residual correction give the quotient, exactly whenever
+        // t/s is representable (a ray sitting on a grid line), within one ulp otherwise.  An
+        // infinite position turns into NaN here and fails the bounds test like the infinity.
+        const double tx = x - c.xd0, ty = y - c.yd0;
+        const double qx = tx * c.inv_sx, qy = ty * c.inv_sy;
+        const double ix = fma(fma(-qx, c.sx, tx), c.inv_sx, qx);
+        const double iy = fma(fma(-qy, c.sy, ty), c.inv_sy, qy);
+        ok = ok && ix >= 0.0 && ix <= (double)(c.nx - 1) && iy >= 0.0 && iy <= (double)(c.ny - 1);   // :248
+        cx1 = cell_of(ix, c.nx); cy1 = cell_of(iy, c.ny);
+        ccell = (size_t)(c.nx - 1) * cy1 + cx1;
+    }
+    // ---- phase 2 ---------------------------------------------------------------------
+    float4 Z = make_float4(0.f, 0.f, 0.f, 0.f), U = Z, V = Z;
+    float2 Gh = make_float2(0.f, 0.f);
+    double2 gu = make_double2(0.0, 0.0), gv = gu;
+    float bxa = 0.f, bxb = 0.f, bya = 0.f, byb = 0.f, cxa = 0.f, cxb = 0.f, cya = 0.f, cyb = 0.f;
+    if (BK == MR_BATHY_GRID) {
+        Z = ldg_f4(brec);
+        Gh = ldg_f2((const float2 *)(brec + 1));
+        if (!UNI) {
+            bxa = __ldg(b.x + bx1); bxb = __ldg(b.x + bx1 + 1);
+            bya = __ldg(b.y + by1); byb = __ldg(b.y + by1 + 1);
+        }
+    }
+    if (CK == MR_CURRENT_GRID) {
+        U = ldg_f4(c.cell_uv + 2 * ccell);
+        V = ldg_f4(c.cell_uv + 2 * ccell + 1);
+        gu = ldg_d2(c.cell_grad + 2 * ccell);
+        gv = ldg_d2(c.cell_grad + 2 * ccell + 1);
+        if (!UNI) {
+            cxa = __ldg(c.xf + cx1); cxb = __ldg(c.xf + cx1 + 1);
+            cya = __ldg(c.yf + cy1); cyb = __ldg(c.yf + cy1 + 1);
+        }
+    }
+    // ---- phase 3 ---------------------------------------------------------------------
+    const double k2 = fma(kx, kx, ky * ky);
+    double k, rk;
+    sqrt_rsqrt(k2, k, rk);
+    const double cs = kx * rk, sn = ky * rk;
+    // ---- phase 4 ---------------------------------------------------------------------
+    float h32, gx32, gy32;
+    if (BK == MR_BATHY_GRID) {
+        if (UNI) {
+            bxa = __fmaf_rn((float)bx1, b.dxf, b.xf0); bxb = __fadd_rn(bxa, b.dxf);
+            bya = __fmaf_rn((float)by1, b.dyf, b.yf0); byb = __fadd_rn(bya, b.dyf);
+        }
+        const CellGeom g = cell_geom<UNI>(bxa, bxb, bya, byb, b.c01, b.c10, xf, yf);
+        const float r = bilinear_eval(g, Z.x, Z.y, Z.z, Z.w);
+        h32 = isn ? qnanf() : r;
+        gx32 = isn ? qnanf() : Gh.x;
+        gy32 = isn ? qnanf() : Gh.y;
+        ok = ok && (isn || g.det_ok);
+    } else {
+        bathy_analytic(BK, b, xf, yf, h32, gx32, gy32);
+    }
+    CurrentVal cv;
+    if (CK == MR_CURRENT_GRID) {
+        if (UNI) {
+            cxa = __fmaf_rn((float)cx1, c.dxf, c.xf0); cxb = __fadd_rn(cxa, c.dxf);
+            cya = __fmaf_rn((float)cy1, c.dyf, c.yf0); cyb = __fadd_rn(cya, c.dyf);
+        }
+        const CellGeom g = cell_geom<UNI>(cxa, cxb, cya, cyb, c.c01, c.c10, xf, yf);
+        cv.u = (double)bilinear_eval(g, U.x, U.y, U.z, U.w);
+        cv.v = (double)bilinear_eval(g, V.x, V.y, V.z, V.w);
+        cv.dudx = gu.x; cv.dudy = gu.y; cv.dvdx = gv.x; cv.dvdy = gv.y;
+        ok = ok && g.det_ok;
+    } else {
+        cv.u = c.u0; cv.v = c.v0; cv.dudx = cv.dudy = cv.dvdx = cv.dvdy = 0.0;   // constant_current.rs:69-77
+    }
+    rhs_f64_fast(kx, ky, k2, k, cs, sn, (double)h32, (double)gx32, (double)gy32, cv, ok, out);
 }
 
 // =============================================================================
@@ -501,11 +624,7 @@ __device__ __forceinline__ void rhs(const BathyDev &b, const CurrentDev &c,
         }
         rhs_f64_strict(kx, ky, (double)h32, (double)gx32, (double)gy32, cv, out);
     } else {
-        bool ok = (BK == MR_BATHY_GRID) ? bathy_grid_fast<UNI>(b, xf, yf, h32, gx32, gy32)
-                                        : bathy_analytic(BK, b, xf, yf, h32, gx32, gy32);
-        if (CK == MR_CURRENT_GRID) ok = current_grid_fast<UNI>(c, x, y, xf, yf, cv) && ok;
-        else { cv.u = c.u0; cv.v = c.v0; cv.dudx = cv.dudy = cv.dvdx = cv.dvdy = 0.0; }   // constant_current.rs:69-77
-        rhs_f64_fast(kx, ky, (double)h32, (double)gx32, (double)gy32, cv, ok, out);
+        rhs_fast<BK, CK, UNI>(b, c, x, y, kx, ky, xf, yf, out);
     }
 }
 

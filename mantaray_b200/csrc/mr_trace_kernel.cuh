@@ -42,6 +42,16 @@ struct TraceArgs {
 
 static constexpr int kBlock = 128;
 
+// build-time tuning knobs (see profiles/): unroll factor of the RK4 stage loop and the
+// resident-blocks-per-SM target of the fast kernel
+#ifndef MR_STAGE_UNROLL
+#define MR_STAGE_UNROLL 1
+#endif
+#ifndef MR_MIN_BLOCKS
+#define MR_MIN_BLOCKS 6
+#endif
+static constexpr int kStageUnroll = MR_STAGE_UNROLL;
+
 __device__ __forceinline__ bool any_nan4(const double y[4])
 {
     return isnan(y[0]) || isnan(y[1]) || isnan(y[2]) || isnan(y[3]);
@@ -52,7 +62,7 @@ __device__ __forceinline__ bool all_nan4(const double y[4])
 }
 
 template <int BK, int CK, int MATH, bool UNI>
-__global__ void __launch_bounds__(kBlock, (MATH == MR_MATH_FAST) ? 5 : 1)
+__global__ void __launch_bounds__(kBlock, (MATH == MR_MATH_FAST) ? MR_MIN_BLOCKS : 1)
 trace_kernel(const __grid_constant__ TraceArgs a)
 {
     const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
@@ -89,7 +99,7 @@ trace_kernel(const __grid_constant__ TraceArgs a)
             double k[4] = {0.0, 0.0, 0.0, 0.0};
             double acc[4] = {-0.0, -0.0, -0.0, -0.0};     // -0 + k0 == k0 for every k0
             bool k0_nan = false;
-#pragma unroll 1
+#pragma unroll kStageUnroll
             for (int st = 0; st < 4; ++st) {
                 const double as = (st == 0) ? 0.0 : (st == 3 ? dt : half);
                 const double ws = (st == 1 || st == 2) ? 2.0 : 1.0;
@@ -97,10 +107,15 @@ trace_kernel(const __grid_constant__ TraceArgs a)
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     const double adv = (MATH == MR_MATH_STRICT) ? __dadd_rn(y[c], __dmul_rn(k[c], as)) : fma(k[c], as, y[c]);
-                    yt[c] = (st == 0) ? y[c] : adv;
+                    // stage 0 evaluates f(y): k is still 0 there, and y + 0*0 == y (a -0 component
+                    // would become +0, which the strict path must not allow)
+                    yt[c] = (MATH == MR_MATH_STRICT && st == 0) ? y[c] : adv;
                 }
                 rhs<BK, CK, MATH, UNI>(a.b, a.c, yt[0], yt[1], yt[2], yt[3], k);
-                if (st == 0) k0_nan = all_nan4(k);
+                if (st == 0) {
+                    k0_nan = all_nan4(k);
+                    if (MATH == MR_MATH_FAST) prefetch_cells<BK, CK>(a.b, a.c, fma(k[0], dt + dt, y[0]), fma(k[1], dt + dt, y[1]));
+                }
 #pragma unroll
                 for (int c = 0; c < 4; ++c)
                     acc[c] = (MATH == MR_MATH_STRICT) ? __dadd_rn(acc[c], __dmul_rn(k[c], ws)) : fma(k[c], ws, acc[c]);

@@ -74,8 +74,40 @@ void run(const char *name, double seed)
     cudaFree(out); cudaFree(cyc);
 }
 
+template <int OP>
+__global__ void lat_kernel(double *out, long long *cycles, double seed)
+{
+    double v = seed + 1e-3 * threadIdx.x;
+    long long t0 = clock64();
+#pragma unroll 16
+    for (int it = 0; it < 4096; ++it) v = op<OP>(v, 0.999999, 1.0000001);
+    long long t1 = clock64();
+    if (v == 12345.678) out[0] = v;
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+template <int OP>
+void lat(const char *name, double seed)
+{
+    double *out; long long *cyc, h;
+    cudaMalloc(&out, 8); cudaMalloc(&cyc, 8);
+    lat_kernel<OP><<<1, 32>>>(out, cyc, seed);
+    cudaDeviceSynchronize();
+    lat_kernel<OP><<<1, 32>>>(out, cyc, seed);
+    cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
+    printf("%-34s %8.2f cycles dependent-issue latency (1 warp)\n", name, (double)h / 4096);
+    cudaFree(out); cudaFree(cyc);
+}
+
 int main()
 {
+    lat<0>("DFMA latency", 1.0);
+    lat<1>("DADD latency", 1.0);
+    lat<2>("DMUL latency", 1.0);
+    lat<6>("f64 1/x latency", 1.3);
+    lat<7>("f64 rsqrt latency", 1.3);
+    lat<9>("f64 exp latency", 0.7);
+    lat<3>("cvt f64->f32->f64+DADD latency", 1.0);
+
     run<0>("DFMA", 1.0);
     run<1>("DADD", 1.0);
     run<2>("DMUL", 1.0);

@@ -115,6 +115,7 @@ static int validate(const mr_bathymetry_desc *b, const mr_current_desc *c)
     case MR_BATHY_CONSTANT: case MR_BATHY_SLOPE: break;
     case MR_BATHY_GRID:
         if (b->nx < 2 || b->ny < 2) return fail(MR_ERR_BAD_ARG, "bathymetry grid needs nx >= 2 and ny >= 2");
+        if ((int64_t)(b->nx - 1) * (b->ny - 1) > 0x7fffffffLL) return fail(MR_ERR_BAD_ARG, "bathymetry grid has more than 2^31 cells");
         if (!b->x || !b->y || !b->depth) return fail(MR_ERR_BAD_ARG, "bathymetry grid: NULL x / y / depth");
         {
             float sx = fabsf(b->x[1] - b->x[0]), sy = fabsf(b->y[1] - b->y[0]);
@@ -132,6 +133,7 @@ static int validate(const mr_bathymetry_desc *b, const mr_current_desc *c)
     case MR_CURRENT_CONSTANT: break;
     case MR_CURRENT_GRID:
         if (c->nx < 2 || c->ny < 2) return fail(MR_ERR_BAD_ARG, "current grid needs nx >= 2 and ny >= 2");
+        if ((int64_t)(c->nx - 1) * (c->ny - 1) > 0x7fffffffLL) return fail(MR_ERR_BAD_ARG, "current grid has more than 2^31 cells");
         if (!c->x || !c->y || !c->u || !c->v) return fail(MR_ERR_BAD_ARG, "current grid: NULL x / y / u / v");
         {
             double sx = fabs(c->x[1] - c->x[0]), sy = fabs(c->y[1] - c->y[0]);
@@ -156,8 +158,10 @@ __global__ void build_bathy_cells(const double *depth, int nx, int ny, double x_
         const double *p = depth + (size_t)nx * y1 + x1;
         const double sw = p[0], se = p[1], nw = p[nx], ne = p[nx + 1];
         cell[2 * i] = make_float4((float)sw, (float)nw, (float)ne, (float)se);
-        cell[2 * i + 1] = make_float4((float)__ddiv_rn(__dsub_rn(se, sw), x_space),
-                                      (float)__ddiv_rn(__dsub_rn(nw, sw), y_space), 0.0f, 0.0f);
+        // `as f32` (cartesian_netcdf3.rs:134) then `as f64` (wave_ray_path.rs:125-126)
+        const double gx = (double)(float)__ddiv_rn(__dsub_rn(se, sw), x_space);
+        const double gy = (double)(float)__ddiv_rn(__dsub_rn(nw, sw), y_space);
+        *reinterpret_cast<double2 *>(cell + 2 * i + 1) = make_double2(gx, gy);
     }
 }
 
@@ -248,6 +252,7 @@ static int upload_fields(DeviceFields &d, const mr_bathymetry_desc *b, const mr_
         build_bathy_cells<<<(unsigned)std::min<size_t>((ncell + 255) / 256, 148 * 16), 256>>>(B.depth, b->nx, b->ny, B.x_space, B.y_space, cell);
         MR_CUDA(cudaGetLastError());
         B.cell = cell;
+        B.nxm1f = (float)(b->nx - 1); B.nym1f = (float)(b->ny - 1);
         B.uniform = affine_f32(b->x, b->nx, &B.dxf) && affine_f32(b->y, b->ny, &B.dyf) &&
                     basis_coeffs(B.dxf, B.dyf, &B.c01, &B.c10) && recip_ok(B.sx, &B.rsx) && recip_ok(B.sy, &B.rsy);
     } else if (b->kind == MR_BATHY_ARRAY) {
@@ -277,6 +282,7 @@ static int upload_fields(DeviceFields &d, const mr_bathymetry_desc *b, const mr_
                                                                                                cell_uv, cell_grad);
         MR_CUDA(cudaGetLastError());
         C.cell_uv = cell_uv;
+        C.nxm1d = (double)(c->nx - 1); C.nym1d = (double)(c->ny - 1);
         C.cell_grad = cell_grad;
         std::vector<float> xf((size_t)c->nx), yf((size_t)c->ny);   // `as f32`, cartesian_current.rs:375-376
         for (int i = 0; i < c->nx; ++i) xf[(size_t)i] = (float)c->x[i];

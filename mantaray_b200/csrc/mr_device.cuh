@@ -43,9 +43,11 @@ struct BathyDev {
     float  sx, sy;             // |x[1]-x[0]|, |y[1]-y[0]| in f32   (cartesian_netcdf3.rs:287)
     float  rsx, rsy;           // RN(1/sx), RN(1/sy); 0 when the exact-division shortcut does not apply
     double x_space, y_space;   // x[1]-x[0] in f64 of the f32 values (cartesian_netcdf3.rs:119-120)
-    // per-cell records for the fast path: cell (x1,y1), x1 < nx-1, y1 < ny-1, two float4 each:
-    //   {z_sw, z_nw, z_ne, z_se} (depth as f32)  and  {dhdx, dhdy, 0, 0} (f32 of the f64 quotient)
+    // per-cell records for the fast path: cell (x1,y1), x1 < nx-1, y1 < ny-1, 32 bytes each:
+    //   float4 {z_sw, z_nw, z_ne, z_se} (depth as f32), double2 {dhdx, dhdy} (the f32 gradient of
+    //   cartesian_netcdf3.rs:134, stored already widened back to f64 as wave_ray_path.rs:125-126 does)
     const float4 *cell;
+    float nxm1f, nym1f;        // (nx-1) as f32, (ny-1) as f32: the bound of cartesian_netcdf3.rs:291
     // coordinates exactly affine in f32 (x[i] == fmaf(i, dxf, x[0]) for every i, same for y):
     // corner coordinates and the change-of-basis coefficients become launch constants
     int32_t uniform;
@@ -67,6 +69,7 @@ struct CurrentDev {
     const float4  *cell_uv;
     const double2 *cell_grad;
     const float *xf, *yf;      // coordinates cast to f32 (cartesian_current.rs:375-376)
+    double nxm1d, nym1d;       // (nx-1), (ny-1) as f64: the bound of cartesian_current.rs:248
     int32_t uniform;
     float xf0, yf0, dxf, dyf, c01, c10;
 };
@@ -80,9 +83,10 @@ static __constant__ double kExpm1C[12] = {
     1.6059043836821613e-10, 2.08767569878681e-09, 2.505210838544172e-08, 2.755731922398589e-07,
     2.7557319223985893e-06, 2.48015873015873e-05, 1.984126984126984e-04, 1.388888888888889e-03,
     8.333333333333333e-03, 4.1666666666666664e-02, 1.6666666666666666e-01, 0.5};
-// {log2(e), 1.5*2^52, ln2_hi, ln2_lo}
-static __constant__ double kExpRed[4] = {1.4426950408889634074, 6755399441055744.0,
-                                         6.93147180369123816490e-01, 1.90821492927058770002e-10};
+// {log2(e), 1.5*2^52, ln2_hi, ln2_lo, -700, G, G/2}
+static __constant__ double kExpRed[7] = {1.4426950408889634074, 6755399441055744.0,
+                                         6.93147180369123816490e-01, 1.90821492927058770002e-10,
+                                         -700.0, 9.8, 4.9};
 
 __device__ __forceinline__ double qnan() { return __longlong_as_double(0x7ff8000000000000LL); }
 __device__ __forceinline__ float  qnanf() { return __int_as_float(0x7fc00000); }
@@ -129,55 +133,26 @@ __device__ __forceinline__ bool bilinear_cell_strict(float xa, float xb, float y
     return true;
 }
 
-// fast form: the cell's geometry (corner coordinates, c01, c10) is resolved once per
-// lookup and shared by every variable interpolated on that cell.
-struct CellGeom {
-    float X, Y;                // fractional coordinates as the reference computes them
-    bool at_xa, at_xb, at_ya, at_yb;   // target coincident with a corner coordinate
-    bool corner;               // ... with a corner point
-    bool det_ok;
-};
-
-template <bool UNI>
-__device__ __forceinline__ CellGeom cell_geom(float xa, float xb, float ya, float yb,
-                                              float c01u, float c10u, float tx, float ty)
-{
-    CellGeom g;
-    float c01, c10;
-    if (UNI) {
-        c01 = c01u; c10 = c10u;
-        g.det_ok = true;
-    } else {
-        float dx = __fsub_rn(xb, xa), dy = __fsub_rn(yb, ya);
-        float det = __fsub_rn(0.0f, __fmul_rn(dx, dy));
-        g.det_ok = det != 0.0f;
-        c01 = -__fdiv_rn(dx, det);
-        c10 = -__fdiv_rn(dy, det);
-    }
-    g.X = __fmul_rn(c01, __fsub_rn(ty, ya));
-    g.Y = __fmul_rn(c10, __fsub_rn(tx, xa));
-    g.at_xa = tx == xa; g.at_xb = tx == xb;
-    g.at_ya = ty == ya; g.at_yb = ty == yb;
-    g.corner = (g.at_xa || g.at_xb) && (g.at_ya || g.at_yb);
-    return g;
-}
-
-__device__ __forceinline__ float bilinear_eval(const CellGeom &g, float zsw, float znw, float zne, float zse)
+// fast form.  The cell's fractional coordinates (X, Y) are resolved once per lookup and
+// shared by every variable interpolated on that cell.
+__device__ __forceinline__ float bilinear_xy(float X, float Y, float zsw, float znw, float zne, float zse)
 {
     float a10 = __fsub_rn(znw, zsw);
     float a01 = __fsub_rn(zse, zsw);
     float a11 = __fsub_rn(__fsub_rn(__fsub_rn(zne, zsw), a10), a01);
-    float r = __fadd_rn(zsw, __fmul_rn(a10, g.X));
-    r = __fadd_rn(r, __fmul_rn(a01, g.Y));
-    r = __fadd_rn(r, __fmul_rn(__fmul_rn(a11, g.X), g.Y));
-    // interpolator.rs:46-50: a target coincident with a corner returns that corner's value,
-    // tested in the order a, b, c, d (later selects take precedence).  Rare: one branch.
-    if (g.corner) {
-        r = (g.at_xb && g.at_ya) ? zse : r;
-        r = (g.at_xb && g.at_yb) ? zne : r;
-        r = (g.at_xa && g.at_yb) ? znw : r;
-        r = (g.at_xa && g.at_ya) ? zsw : r;
-    }
+    float r = __fadd_rn(zsw, __fmul_rn(a10, X));
+    r = __fadd_rn(r, __fmul_rn(a01, Y));
+    return __fadd_rn(r, __fmul_rn(__fmul_rn(a11, X), Y));
+}
+// interpolator.rs:46-50: a target coincident with a corner returns that corner's value, tested in
+// the order a, b, c, d (the later selects below take precedence).
+__device__ __forceinline__ float corner_pick(float r, bool at_xa, bool at_xb, bool at_ya, bool at_yb,
+                                             float zsw, float znw, float zne, float zse)
+{
+    r = (at_xb && at_ya) ? zse : r;
+    r = (at_xb && at_yb) ? zne : r;
+    r = (at_xa && at_yb) ? znw : r;
+    r = (at_xa && at_ya) ? zsw : r;
     return r;
 }
 
@@ -462,19 +437,19 @@ __device__ __forceinline__ void exp_expm1_neg(double z, double &E, double &em)
 //   E = exp(-2kh), m = 1-E = -expm1(-2kh), w = 1+E
 //   tanh kh = m/w,  1/cosh^2 kh = 4E/w^2,  1/(sinh kh cosh kh) = 4E/(m w)
 // and cos(theta) = kx/k, sin(theta) = ky/k instead of atan2 + sincos.
-// Special values follow the reference: h <= 0, h NaN, k == 0, k NaN -> four NaN;
-// large kh: E -> 0, tanh = 1, second cg term 0, bathymetric term -0 (the reference
-// gets the same from cosh^2 -> inf and sinh -> inf).
-__device__ __forceinline__ void rhs_f64_fast(double kx, double ky, double k2, double k, double cs, double sn,
+// Every case in which the reference's RHS is four NaNs (field lookup Err, h <= 0, h NaN,
+// k == 0, k NaN) reaches this function as h = NaN and leaves it as four NaNs by plain NaN
+// propagation, so there is no per-output select.  Large kh: E -> 0, tanh = 1, second cg term
+// 0, bathymetric term -0 (the reference gets the same from cosh^2 -> inf and sinh -> inf).
+__device__ __forceinline__ void rhs_f64_fast(double kx, double ky, double k, double cs, double sn,
                                              double h, double dhdx, double dhdy,
-                                             const CurrentVal &cv, bool fields_ok, double out[4])
+                                             const CurrentVal &cv, double out[4])
 {
-    const bool ok = fields_ok && (h > 0.0) && (k2 > 0.0);        // false for NaN h / NaN k as well
-    // h = +inf: the reference's cg is inf/inf = NaN while its bathymetric term is -0
-    const bool cg_ok = ok && (h < __longlong_as_double(0x7ff0000000000000LL));
     const double kh = k * h;
+    double z = -2.0 * kh;
+    z = (z < kExpRed[4]) ? kExpRed[4] : z;    // E underflows anyway; NaN stays NaN
     double E, em;
-    exp_expm1_neg(fmax(-2.0 * kh, -700.0), E, em);
+    exp_expm1_neg(z, E, em);
     const double m = -em, w = 2.0 + em;
     const double r = recip(m * w);
     const double invw = m * r;
@@ -482,16 +457,15 @@ __device__ __forceinline__ void rhs_f64_fast(double kx, double ky, double k2, do
     const double E4 = 4.0 * E;
     const double sech2 = (E4 * invw) * invw;
     const double csch_sech = E4 * r;
-    const double q = (k * kG) * T;
+    const double q = (k * kExpRed[5]) * T;
     double sq, rq;
     sqrt_rsqrt(q, sq, rq);
-    const double cg = (kG * 0.5) * (fma(kh, sech2, T) * rq);
+    const double cg = kExpRed[6] * (fma(kh, sech2, T) * rq);
     const double Bc = ((-0.5 * k) * csch_sech) * sq;
-    const double nan = qnan();
-    out[0] = cg_ok ? fma(cg, cs, cv.u) : nan;
-    out[1] = cg_ok ? fma(cg, sn, cv.v) : nan;
-    out[2] = ok ? fma(-ky, cv.dvdx, fma(-kx, cv.dudx, Bc * dhdx)) : nan;
-    out[3] = ok ? fma(-ky, cv.dvdy, fma(-kx, cv.dudy, Bc * dhdy)) : nan;
+    out[0] = fma(cg, cs, cv.u);
+    out[1] = fma(cg, sn, cv.v);
+    out[2] = fma(-ky, cv.dvdx, fma(-kx, cv.dudx, Bc * dhdx));
+    out[3] = fma(-ky, cv.dvdy, fma(-kx, cv.dudy, Bc * dhdy));
 }
 
 // =============================================================================
@@ -501,6 +475,11 @@ __device__ __forceinline__ void rhs_f64_fast(double kx, double ky, double k2, do
 //   2. all record loads
 //   3. the wavenumber-only f64 work (k, 1/k, direction cosines) under the loads
 //   4. f32 bilinears, then the f64 stage
+// A failed lookup (out of bounds, NaN index, degenerate cell) is not branched on: the cell
+// index is clamped so the loads stay in bounds, and the depth handed to the f64 stage is
+// replaced by NaN, which makes all four outputs NaN exactly as wave_ray_path.rs:222-228 does.
+// A NaN position needs no special case either: the reference's Ok(NaN depth) also ends in four
+// NaNs (cg and the bathymetric term are NaN), and a NaN index fails the bounds test here.
 // =============================================================================
 template <int BK, int CK, bool UNI>
 __device__ __forceinline__ void rhs_fast(const BathyDev &b, const CurrentDev &c,
@@ -509,10 +488,9 @@ __device__ __forceinline__ void rhs_fast(const BathyDev &b, const CurrentDev &c,
 {
     // ---- phase 1 ---------------------------------------------------------------------
     bool ok = true;
-    const bool isn = isnan(xf) || isnan(yf);
     int bx1 = 0, by1 = 0, cx1 = 0, cy1 = 0;
     const float4 *brec = nullptr;
-    size_t ccell = 0;
+    unsigned ccell = 0;
     if (BK == MR_BATHY_GRID) {
         float ix, iy;                                                          // cartesian_netcdf3.rs:289
         if (UNI) {
@@ -522,10 +500,9 @@ __device__ __forceinline__ void rhs_fast(const BathyDev &b, const CurrentDev &c,
             ix = __fdiv_rn(__fsub_rn(xf, b.xf0), b.sx);
             iy = __fdiv_rn(__fsub_rn(yf, b.yf0), b.sy);
         }
-        // :291 out of bounds -> Err; :101-103 NaN position -> Ok(NaN, (NaN, NaN))
-        ok = isn || (ix >= 0.0f && ix <= (float)(b.nx - 1) && iy >= 0.0f && iy <= (float)(b.ny - 1));
+        ok = ix >= 0.0f && ix <= b.nxm1f && iy >= 0.0f && iy <= b.nym1f;      // :291
         bx1 = cell_of(ix, b.nx); by1 = cell_of(iy, b.ny);
-        brec = b.cell + 2 * ((size_t)(b.nx - 1) * by1 + bx1);
+        brec = b.cell + 2u * (unsigned)((b.nx - 1) * by1 + bx1);
     }
     if (CK == MR_CURRENT_GRID) {
         // f64 fractional index (cartesian_current.rs:246).  The spacing is a launch constant:
@@ -536,28 +513,27 @@ __device__ __forceinline__ void rhs_fast(const BathyDev &b, const CurrentDev &c,
         const double qx = tx * c.inv_sx, qy = ty * c.inv_sy;
         const double ix = fma(fma(-qx, c.sx, tx), c.inv_sx, qx);
         const double iy = fma(fma(-qy, c.sy, ty), c.inv_sy, qy);
-        ok = ok && ix >= 0.0 && ix <= (double)(c.nx - 1) && iy >= 0.0 && iy <= (double)(c.ny - 1);   // :248
+        ok = ok && ix >= 0.0 && ix <= c.nxm1d && iy >= 0.0 && iy <= c.nym1d;  // :248
         cx1 = cell_of(ix, c.nx); cy1 = cell_of(iy, c.ny);
-        ccell = (size_t)(c.nx - 1) * cy1 + cx1;
+        ccell = (unsigned)((c.nx - 1) * cy1 + cx1);
     }
     // ---- phase 2 ---------------------------------------------------------------------
     float4 Z = make_float4(0.f, 0.f, 0.f, 0.f), U = Z, V = Z;
-    float2 Gh = make_float2(0.f, 0.f);
-    double2 gu = make_double2(0.0, 0.0), gv = gu;
+    double2 gh = make_double2(0.0, 0.0), gu = gh, gv = gh;
     float bxa = 0.f, bxb = 0.f, bya = 0.f, byb = 0.f, cxa = 0.f, cxb = 0.f, cya = 0.f, cyb = 0.f;
     if (BK == MR_BATHY_GRID) {
         Z = ldg_f4(brec);
-        Gh = ldg_f2((const float2 *)(brec + 1));
+        gh = ldg_d2((const double2 *)(brec + 1));
         if (!UNI) {
             bxa = __ldg(b.x + bx1); bxb = __ldg(b.x + bx1 + 1);
             bya = __ldg(b.y + by1); byb = __ldg(b.y + by1 + 1);
         }
     }
     if (CK == MR_CURRENT_GRID) {
-        U = ldg_f4(c.cell_uv + 2 * ccell);
-        V = ldg_f4(c.cell_uv + 2 * ccell + 1);
-        gu = ldg_d2(c.cell_grad + 2 * ccell);
-        gv = ldg_d2(c.cell_grad + 2 * ccell + 1);
+        U = ldg_f4(c.cell_uv + 2u * ccell);
+        V = ldg_f4(c.cell_uv + 2u * ccell + 1);
+        gu = ldg_d2(c.cell_grad + 2u * ccell);
+        gv = ldg_d2(c.cell_grad + 2u * ccell + 1);
         if (!UNI) {
             cxa = __ldg(c.xf + cx1); cxb = __ldg(c.xf + cx1 + 1);
             cya = __ldg(c.yf + cy1); cyb = __ldg(c.yf + cy1 + 1);
@@ -569,36 +545,63 @@ __device__ __forceinline__ void rhs_fast(const BathyDev &b, const CurrentDev &c,
     sqrt_rsqrt(k2, k, rk);
     const double cs = kx * rk, sn = ky * rk;
     // ---- phase 4 ---------------------------------------------------------------------
-    float h32, gx32, gy32;
+    float h32;
+    double dhdx, dhdy;
     if (BK == MR_BATHY_GRID) {
+        float c01 = b.c01, c10 = b.c10;
         if (UNI) {
             bxa = __fmaf_rn((float)bx1, b.dxf, b.xf0); bxb = __fadd_rn(bxa, b.dxf);
             bya = __fmaf_rn((float)by1, b.dyf, b.yf0); byb = __fadd_rn(bya, b.dyf);
+        } else {
+            const float dx = __fsub_rn(bxb, bxa), dy = __fsub_rn(byb, bya);
+            const float det = __fsub_rn(0.0f, __fmul_rn(dx, dy));              // interpolator.rs:64
+            ok = ok && det != 0.0f;                                            // :65-67
+            c01 = -__fdiv_rn(dx, det); c10 = -__fdiv_rn(dy, det);              // :70-71
         }
-        const CellGeom g = cell_geom<UNI>(bxa, bxb, bya, byb, b.c01, b.c10, xf, yf);
-        const float r = bilinear_eval(g, Z.x, Z.y, Z.z, Z.w);
-        h32 = isn ? qnanf() : r;
-        gx32 = isn ? qnanf() : Gh.x;
-        gy32 = isn ? qnanf() : Gh.y;
-        ok = ok && (isn || g.det_ok);
+        const float X = __fmul_rn(c01, __fsub_rn(yf, bya)), Y = __fmul_rn(c10, __fsub_rn(xf, bxa));
+        h32 = bilinear_xy(X, Y, Z.x, Z.y, Z.z, Z.w);
+        if (xf == bxa || xf == bxb) {
+            const bool at_ya = yf == bya, at_yb = yf == byb;
+            if (at_ya || at_yb) h32 = corner_pick(h32, xf == bxa, xf == bxb, at_ya, at_yb, Z.x, Z.y, Z.z, Z.w);
+        }
+        dhdx = gh.x; dhdy = gh.y;
     } else {
+        float gx32, gy32;
         bathy_analytic(BK, b, xf, yf, h32, gx32, gy32);
+        dhdx = (double)gx32; dhdy = (double)gy32;
     }
     CurrentVal cv;
     if (CK == MR_CURRENT_GRID) {
+        float c01 = c.c01, c10 = c.c10;
         if (UNI) {
             cxa = __fmaf_rn((float)cx1, c.dxf, c.xf0); cxb = __fadd_rn(cxa, c.dxf);
             cya = __fmaf_rn((float)cy1, c.dyf, c.yf0); cyb = __fadd_rn(cya, c.dyf);
+        } else {
+            const float dx = __fsub_rn(cxb, cxa), dy = __fsub_rn(cyb, cya);
+            const float det = __fsub_rn(0.0f, __fmul_rn(dx, dy));
+            ok = ok && det != 0.0f;
+            c01 = -__fdiv_rn(dx, det); c10 = -__fdiv_rn(dy, det);
         }
-        const CellGeom g = cell_geom<UNI>(cxa, cxb, cya, cyb, c.c01, c.c10, xf, yf);
-        cv.u = (double)bilinear_eval(g, U.x, U.y, U.z, U.w);
-        cv.v = (double)bilinear_eval(g, V.x, V.y, V.z, V.w);
+        const float X = __fmul_rn(c01, __fsub_rn(yf, cya)), Y = __fmul_rn(c10, __fsub_rn(xf, cxa));
+        float u32 = bilinear_xy(X, Y, U.x, U.y, U.z, U.w);
+        float v32 = bilinear_xy(X, Y, V.x, V.y, V.z, V.w);
+        if (xf == cxa || xf == cxb) {
+            const bool at_ya = yf == cya, at_yb = yf == cyb;
+            if (at_ya || at_yb) {
+                u32 = corner_pick(u32, xf == cxa, xf == cxb, at_ya, at_yb, U.x, U.y, U.z, U.w);
+                v32 = corner_pick(v32, xf == cxa, xf == cxb, at_ya, at_yb, V.x, V.y, V.z, V.w);
+            }
+        }
+        cv.u = (double)u32; cv.v = (double)v32;
         cv.dudx = gu.x; cv.dudy = gu.y; cv.dvdx = gv.x; cv.dvdy = gv.y;
-        ok = ok && g.det_ok;
     } else {
         cv.u = c.u0; cv.v = c.v0; cv.dudx = cv.dudy = cv.dvdx = cv.dvdy = 0.0;   // constant_current.rs:69-77
     }
-    rhs_f64_fast(kx, ky, k2, k, cs, sn, (double)h32, (double)gx32, (double)gy32, cv, ok, out);
+    // h <= 0 -> cg = NaN and the bathymetric term is NaN too (inf*0 or sqrt of a negative);
+    // k == 0 -> Err (wave_ray_path.rs:178-183): all four NaN, like a failed lookup
+    ok = ok && h32 > 0.0f && k2 > 0.0;
+    const double h = ok ? (double)h32 : qnan();
+    rhs_f64_fast(kx, ky, k, cs, sn, h, dhdx, dhdy, cv, out);
 }
 
 // =============================================================================

@@ -48,7 +48,7 @@ static constexpr int kBlock = 128;
 #define MR_STAGE_UNROLL 1
 #endif
 #ifndef MR_MIN_BLOCKS
-#define MR_MIN_BLOCKS 6
+#define MR_MIN_BLOCKS 7
 #endif
 static constexpr int kStageUnroll = MR_STAGE_UNROLL;
 
@@ -90,10 +90,11 @@ trace_kernel(const __grid_constant__ TraceArgs a)
         a.fin[i] = qnan(); a.fin[a.n + i] = qnan(); a.fin[2 * a.n + i] = qnan(); a.fin[3 * a.n + i] = qnan();
     }
 
-    int64_t s = 1;
+    const int32_t nsteps = (int32_t)a.nsteps;      // < 2^31 (mr_num_steps)
     int32_t until_store = a.stride;        // counts down to the next stored row
-    int64_t row = 0;                       // last stored row index
-    for (; s <= a.nsteps; ++s) {
+    int64_t o = i;                         // offset of this ray in the last stored row
+    int32_t rows_left = nsteps / a.stride; // stored rows still to write
+    for (int32_t s = 1; s <= nsteps; ++s) {
         if (!__any_sync(0xffffffffu, alive)) break;
         if (alive) {
             double k[4] = {0.0, 0.0, 0.0, 0.0};
@@ -112,10 +113,7 @@ trace_kernel(const __grid_constant__ TraceArgs a)
                     yt[c] = (MATH == MR_MATH_STRICT && st == 0) ? y[c] : adv;
                 }
                 rhs<BK, CK, MATH, UNI>(a.b, a.c, yt[0], yt[1], yt[2], yt[3], k);
-                if (st == 0) {
-                    k0_nan = all_nan4(k);
-                    if (MATH == MR_MATH_FAST) prefetch_cells<BK, CK>(a.b, a.c, fma(k[0], dt + dt, y[0]), fma(k[1], dt + dt, y[1]));
-                }
+                if (st == 0) k0_nan = all_nan4(k);
 #pragma unroll
                 for (int c = 0; c < 4; ++c)
                     acc[c] = (MATH == MR_MATH_STRICT) ? __dadd_rn(acc[c], __dmul_rn(k[c], ws)) : fma(k[c], ws, acc[c]);
@@ -124,36 +122,36 @@ trace_kernel(const __grid_constant__ TraceArgs a)
 #pragma unroll
             for (int c = 0; c < 4; ++c)
                 yn[c] = (MATH == MR_MATH_STRICT) ? __dadd_rn(y[c], __dmul_rn(acc[c], sixth)) : fma(acc[c], sixth, y[c]);
-            rows = (int32_t)(s + 1);
+            rows = s + 1;
+            const bool n0 = isnan(yn[0]), n1 = isnan(yn[1]), n2 = isnan(yn[2]), n3 = isnan(yn[3]);
             if (clean) {
-                if (any_nan4(yn)) {
+                if (n0 || n1 || n2 || n3) {
                     clean = false;
                     if (a.fin) {           // y is the last NaN-free row
                         a.fin[i] = y[0]; a.fin[a.n + i] = y[1]; a.fin[2 * a.n + i] = y[2]; a.fin[3 * a.n + i] = y[3];
                     }
                 } else {
-                    len = (int32_t)(s + 1);
+                    len = s + 1;
                 }
             }
 #pragma unroll
             for (int c = 0; c < 4; ++c) y[c] = yn[c];
-            if (k0_nan || all_nan4(y)) alive = false;    // solout
+            if (k0_nan || (n0 && n1 && n2 && n3)) alive = false;    // solout
         }
         if (--until_store == 0) {
             until_store = a.stride;
-            ++row;
+            o += a.ld;
+            --rows_left;
             if (store) {
-                const int64_t o = row * a.ld + i;
                 a.x[o] = y[0]; a.y[o] = y[1]; a.kx[o] = y[2]; a.ky[o] = y[3];
             }
         }
     }
     // whole warp stopped: rows it never reached are NaN
     if (store) {
-        const int64_t last_row = a.nsteps / a.stride;
         const double nan = qnan();
-        for (++row; row <= last_row; ++row) {
-            const int64_t o = row * a.ld + i;
+        for (; rows_left > 0; --rows_left) {
+            o += a.ld;
             a.x[o] = nan; a.y[o] = nan; a.kx[o] = nan; a.ky[o] = nan;
         }
     }

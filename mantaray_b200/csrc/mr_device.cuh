@@ -83,10 +83,10 @@ static __constant__ double kExpm1C[12] = {
     1.6059043836821613e-10, 2.08767569878681e-09, 2.505210838544172e-08, 2.755731922398589e-07,
     2.7557319223985893e-06, 2.48015873015873e-05, 1.984126984126984e-04, 1.388888888888889e-03,
     8.333333333333333e-03, 4.1666666666666664e-02, 1.6666666666666666e-01, 0.5};
-// {log2(e), 1.5*2^52, ln2_hi, ln2_lo, -700, G, G/2}
+// {log2(e), 1.5*2^52, ln2_hi, ln2_lo, deep-water threshold on kh, G, G/2}
 static __constant__ double kExpRed[7] = {1.4426950408889634074, 6755399441055744.0,
                                          6.93147180369123816490e-01, 1.90821492927058770002e-10,
-                                         -700.0, 9.8, 4.9};
+                                         22.0, 9.8, 4.9};
 
 __device__ __forceinline__ double qnan() { return __longlong_as_double(0x7ff8000000000000LL); }
 __device__ __forceinline__ float  qnanf() { return __int_as_float(0x7fc00000); }
@@ -412,7 +412,7 @@ __device__ __forceinline__ double recip(double x)
     return fma(r0, e, r0);
 }
 
-// E = exp(z) and em = expm1(z) for z in [-700, 0] (z is clamped by the caller).
+// E = exp(z) and em = expm1(z) for z in [-44, 0] (larger kh takes the deep-water branch).
 // z = n ln2 + r, |r| <= ln2/2;  expm1(r) = r + r^2 P(r) (Taylor through r^13, remainder
 // < 2e-17 relative);  E = 2^n (1 + p),  em = 2^n p + (2^n - 1)  (2^n - 1 is exact).
 __device__ __forceinline__ void exp_expm1_neg(double z, double &E, double &em)
@@ -427,7 +427,7 @@ __device__ __forceinline__ void exp_expm1_neg(double z, double &E, double &em)
 #pragma unroll
     for (int i = 1; i < 12; ++i) p = fma(p, r, kExpm1C[i]);
     p = fma(r * r, p, r);                          // expm1(r)
-    double s = __hiloint2double((n + 1023) << 20, 0);   // 2^n, n in [-1010, 0]
+    double s = __hiloint2double((n + 1023) << 20, 0);   // 2^n, n in [-64, 0]
     E = fma(s, p, s);
     em = fma(s, p, s - 1.0);
 }
@@ -446,21 +446,26 @@ __device__ __forceinline__ void rhs_f64_fast(double kx, double ky, double k, dou
                                              const CurrentVal &cv, double out[4])
 {
     const double kh = k * h;
-    double z = -2.0 * kh;
-    z = (z < kExpRed[4]) ? kExpRed[4] : z;    // E underflows anyway; NaN stays NaN
-    double E, em;
-    exp_expm1_neg(z, E, em);
-    const double m = -em, w = 2.0 + em;
-    const double r = recip(m * w);
-    const double invw = m * r;
-    const double T = m * invw;                // tanh(kh)
-    const double E4 = 4.0 * E;
-    const double sech2 = (E4 * invw) * invw;
-    const double csch_sech = E4 * r;
+    double T = 1.0, hs2 = 0.0, csch_sech = 0.0;      // tanh kh, kh/cosh^2 kh, 1/(sinh kh cosh kh)
+    // Deep water, kh >= 22: exp(-2kh) < 8e-20, so in f64 tanh kh == 1 exactly, kh/cosh^2 kh <
+    // 2^-57 vanishes against it, and the bathymetric term changes k by less than 3e-18 of itself
+    // per step — below half an ulp, i.e. the reference's own sum rounds it away.  The
+    // exponential is skipped there.  (NaN kh takes the general branch and propagates.)
+    if (!(kh >= kExpRed[4])) {
+        double E, em;
+        exp_expm1_neg(-2.0 * kh, E, em);
+        const double m = -em, w = 2.0 + em;
+        const double r = recip(m * w);
+        const double invw = m * r;
+        T = m * invw;
+        const double E4 = 4.0 * E;
+        hs2 = kh * ((E4 * invw) * invw);
+        csch_sech = E4 * r;
+    }
     const double q = (k * kExpRed[5]) * T;
     double sq, rq;
     sqrt_rsqrt(q, sq, rq);
-    const double cg = kExpRed[6] * (fma(kh, sech2, T) * rq);
+    const double cg = kExpRed[6] * ((T + hs2) * rq);
     const double Bc = ((-0.5 * k) * csch_sech) * sq;
     out[0] = fma(cg, cs, cv.u);
     out[1] = fma(cg, sn, cv.v);

@@ -51,6 +51,47 @@ __global__ void __launch_bounds__(1024) k(double *out, long long *cycles, double
     if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
 }
 
+// DFMA / DMUL / DADD with every operand a distinct live register (register-file read bandwidth)
+__global__ void __launch_bounds__(1024) k3reg(double *out, long long *cycles, double seed, int mode)
+{
+    double v[CHAINS], b[CHAINS], c[CHAINS];
+#pragma unroll
+    for (int i = 0; i < CHAINS; ++i) { v[i] = seed + 1e-3 * (threadIdx.x + i); b[i] = 0.999999 + 1e-9 * (threadIdx.x + i); c[i] = 1e-7 * (i + 1 + threadIdx.x); }
+    long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < ITERS; ++it) {
+        if (mode == 0) {
+#pragma unroll
+            for (int i = 0; i < CHAINS; ++i) v[i] = fma(v[i], b[i], c[i]);
+        } else if (mode == 1) {
+#pragma unroll
+            for (int i = 0; i < CHAINS; ++i) v[i] = fma(v[i], b[i], v[(i + 1) % CHAINS]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < CHAINS; ++i) v[i] = __dmul_rn(v[i], b[i]);
+        }
+    }
+    long long t1 = clock64();
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < CHAINS; ++i) s += v[i] + b[i] + c[i];
+    if (s == 12345.678) out[0] = s;
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+void run3(const char *name, int mode)
+{
+    int sms = 0; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    int blocks = sms * 2;
+    double *out; long long *cyc;
+    cudaMalloc(&out, 8); cudaMalloc(&cyc, 8 * blocks);
+    k3reg<<<blocks, 1024>>>(out, cyc, 1.0, mode); cudaDeviceSynchronize();
+    k3reg<<<blocks, 1024>>>(out, cyc, 1.0, mode); cudaDeviceSynchronize();
+    long long h[1024]; cudaMemcpy(h, cyc, 8 * (blocks < 1024 ? blocks : 1024), cudaMemcpyDeviceToHost);
+    double avg = 0; for (int i = 0; i < blocks && i < 1024; ++i) avg += h[i]; avg /= blocks;
+    printf("%-34s %8.2f thread-ops/clk/SM\n", name, 2.0 * 1024 * CHAINS * ITERS / avg);
+    cudaFree(out); cudaFree(cyc);
+}
+
 template <int OP>
 void run(const char *name, double seed)
 {
@@ -100,6 +141,9 @@ void lat(const char *name, double seed)
 
 int main()
 {
+    run3("DFMA 3 distinct regs", 0);
+    run3("DFMA 3 regs, cross-chain", 1);
+    run3("DMUL 2 distinct regs", 2);
     lat<0>("DFMA latency", 1.0);
     lat<1>("DADD latency", 1.0);
     lat<2>("DMUL latency", 1.0);

@@ -256,6 +256,13 @@ void mr_host_free(void *p);
  * measurement plumbing, not part of the path. */
 int  mr_measure_fp64_peak(int device, int millis, double *tflops);
 
+/* Self-test of the fast path's exact f32 division by a launch constant (the fractional
+ * index of src/bathymetry/cartesian_netcdf3.rs:289): compares it with the IEEE divide for
+ * EVERY non-negative finite float t, for the divisor `spacing`, on `device`.  *mismatches
+ * receives the number of t whose quotients differ in any bit (NaN/inf classes compared as
+ * classes); *usable receives 0 if the library would not use the shortcut for this spacing. */
+int  mr_selftest_fdiv(int device, float spacing, uint64_t *mismatches, int32_t *usable);
+
 #ifdef __cplusplus
 }
 #endif

@@ -129,6 +129,7 @@ SIGNATURES = {
     "mr_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
     "mr_host_free": (None, [C.c_void_p]),
     "mr_measure_fp64_peak": (C.c_int, [C.c_int, C.c_int, c_double_p]),
+    "mr_selftest_fdiv": (C.c_int, [C.c_int, C.c_float, C.POINTER(C.c_uint64), c_int32_p]),
 }
 
 

@@ -67,6 +67,22 @@ cudaError_t launch_dfma_probe(double *sink, int iters, int blocks, cudaStream_t 
     return cudaGetLastError();
 }
 
+// ---- exhaustive check of fdiv_const ---------------------------------------------
+__global__ void fdiv_selftest_kernel(float s, float r, unsigned long long *bad)
+{
+    unsigned long long local = 0;
+    // every non-negative finite float: bit patterns 0 .. 0x7f7fffff
+    for (unsigned long long b = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; b <= 0x7f7fffffull;
+         b += (unsigned long long)gridDim.x * blockDim.x) {
+        const float t = __uint_as_float((unsigned)b);
+        const float want = __fdiv_rn(t, s), got = fdiv_const(t, s, r);
+        const bool same = (__float_as_uint(want) == __float_as_uint(got)) || (isinf(want) && !(got == got)) ||
+                          (!(want == want) && !(got == got));
+        local += same ? 0 : 1;
+    }
+    if (local) atomicAdd(bad, local);
+}
+
 // ---- field handle -----------------------------------------------------------
 struct DeviceFields {
     int dev = -1;
@@ -757,6 +773,29 @@ int mr_measure_fp64_peak(int device, int millis, double *tflops)
     cudaFree(sink);
     if (cur != device) cudaSetDevice(cur);
     *tflops = best;
+    return MR_OK;
+}
+
+int mr_selftest_fdiv(int device, float spacing, uint64_t *mismatches, int32_t *usable)
+{
+    if (!mismatches || !usable) return fail(MR_ERR_BAD_ARG, "mr_selftest_fdiv: NULL output");
+    *mismatches = 0;
+    float r = 0.f;
+    *usable = recip_ok(spacing, &r) ? 1 : 0;
+    if (!*usable) return MR_OK;
+    if (device < 0 || device >= device_count_quiet()) return fail(MR_ERR_CUDA, "mr_selftest_fdiv: no such CUDA device");
+    int cur = -1;
+    MR_CUDA(cudaGetDevice(&cur));
+    MR_CUDA(cudaSetDevice(device));
+    unsigned long long *bad = nullptr, h = 0;
+    MR_CUDA(cudaMalloc(&bad, sizeof(*bad)));
+    MR_CUDA(cudaMemset(bad, 0, sizeof(*bad)));
+    fdiv_selftest_kernel<<<148 * 32, 256>>>(spacing, r, bad);
+    MR_CUDA(cudaGetLastError());
+    MR_CUDA(cudaMemcpy(&h, bad, sizeof(h), cudaMemcpyDeviceToHost));
+    cudaFree(bad);
+    if (cur != device) cudaSetDevice(cur);
+    *mismatches = h;
     return MR_OK;
 }
 

@@ -1,0 +1,79 @@
+"""The C-ABI library loads on a box without a GPU and exports exactly what the header declares."""
+
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from mantaray_b200 import _abi, _capi
+from mantaray_b200 import ConstantCurrent, ConstantDepth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "mantaray_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mr_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_and_binding_agree():
+    assert header_functions() == sorted(_abi.SIGNATURES)
+
+
+def test_library_exports_every_symbol():
+    lib = C.CDLL(_capi.lib_path())
+    for name in header_functions():
+        assert hasattr(lib, name), f"{name} is declared in include/mantaray_b200.h but not exported"
+    assert _capi.load().mr_abi_version() == 1
+
+
+def test_struct_layouts_match_c():
+    """sizeof/offsets as a C compiler lays the header's structs out (LP64)."""
+    assert C.sizeof(_abi.BathymetryDesc) == 72 and _abi.BathymetryDesc.x.offset == 16 and _abi.BathymetryDesc.h0.offset == 48
+    assert C.sizeof(_abi.CurrentDesc) == 64 and _abi.CurrentDesc.x.offset == 16 and _abi.CurrentDesc.u0.offset == 48
+    assert C.sizeof(_abi.TraceOpts) == 16
+
+
+def test_sizes_without_gpu():
+    lib = _capi.load()
+    assert lib.mr_num_steps(0.0, 10.0, 2.0) == 5 and lib.mr_num_rows(0.0, 10.0, 2.0, 1) == 6
+    assert lib.mr_num_steps(0.0, 10.0, 3.0) == 4                 # ceil
+    assert lib.mr_num_rows(0.0, 10.0, 1.0, 4) == 3 and lib.mr_num_rows(0.0, 10.0, 1.0, 0) == 11
+    assert lib.mr_num_steps(100.0, 102.0, 1.0) == 2              # t0 != 0 (src/ray.rs tests)
+    for bad in [(0.0, 10.0, 0.0), (0.0, 10.0, -1.0), (0.0, -10.0, 1.0), (0.0, float("nan"), 1.0), (0.0, 1e30, 1e-3)]:
+        assert lib.mr_num_steps(*bad) == -1
+
+
+@pytest.mark.skipif(_capi.device_count() > 0, reason="needs a box WITHOUT a GPU")
+def test_compute_fails_loudly_without_gpu():
+    """No CPU fallback: every compute entry point reports MR_ERR_CUDA."""
+    with pytest.raises(_capi.MantarayError) as e:
+        _capi.Fields(ConstantDepth(10.0), ConstantCurrent(0, 0))
+    assert e.value.code == _abi.MR_ERR_CUDA and "no CPU fallback" in e.value.message
+    v = C.c_double()
+    assert _capi.load().mr_measure_fp64_peak(0, 10, C.byref(v)) == _abi.MR_ERR_CUDA
+    p = C.c_void_p()
+    assert _capi.load().mr_host_alloc(16, C.byref(p)) == _abi.MR_ERR_CUDA
+
+
+def test_descriptor_validation_messages():
+    lib = _capi.load()
+    h = C.c_void_p()
+    b = ConstantDepth(10.0).to_desc()
+    c = ConstantCurrent(0, 0).to_desc()
+    b.kind = 9
+    assert lib.mr_fields_create(C.byref(b), C.byref(c), 1, C.byref(h)) == _abi.MR_ERR_BAD_ARG
+    assert b"unknown bathymetry kind" in lib.mr_last_error()
+    b = _abi.BathymetryDesc(kind=_abi.MR_BATHY_GRID, nx=1, ny=5)
+    assert lib.mr_fields_create(C.byref(b), C.byref(c), 1, C.byref(h)) == _abi.MR_ERR_BAD_ARG
+    assert b"nx >= 2" in lib.mr_last_error()
+    x = np.zeros(3, dtype=np.float32)                           # zero spacing
+    d = np.zeros(9)
+    b = _abi.BathymetryDesc(kind=_abi.MR_BATHY_GRID, nx=3, ny=3, x=x.ctypes.data_as(_abi.c_float_p),
+                            y=x.ctypes.data_as(_abi.c_float_p), depth=d.ctypes.data_as(_abi.c_double_p))
+    assert lib.mr_fields_create(C.byref(b), C.byref(c), 1, C.byref(h)) == _abi.MR_ERR_BAD_ARG
+    assert lib.mr_fields_create(None, C.byref(c), 1, C.byref(h)) == _abi.MR_ERR_BAD_ARG
+    assert lib.mr_trace_many(None, 1, None, None, None, None, 0.0, 1.0, 1.0, None, *([None] * 8)) == _abi.MR_ERR_BAD_ARG

@@ -1,0 +1,165 @@
+"""The reference-facing surface on the GPU: `mantaray.single_ray` / `mantaray.ray_tracing` through
+NetCDF files (ports of python/tests/test_core.py), the file-opening entry point, the exact f32
+division self-test, pinned buffers and the multi-device handle."""
+
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import mantaray
+import mantaray_b200
+from conftest import assert_parity
+from mantaray_b200 import CartesianCurrent, CartesianNetcdf3, Fields, _abi, _capi, trace_many
+from mantaray_b200 import workloads as W
+from mantaray_b200.io_utility import write_netcdf3
+
+pytestmark = pytest.mark.gpu
+
+
+# ---- python/tests/test_core.py:9-37 fixtures: 3x3 grids, data declared (x, y) -------------------------
+@pytest.fixture
+def island_and_current(tmp_path):
+    x = np.array([-1e4, 0.0, 1e4])
+    write_netcdf3(tmp_path / "island.nc", [("x", 3), ("y", 3)],
+                  {"x": (["x"], x), "y": (["y"], x), "depth": (["x", "y"], 10_000.0 * np.ones((3, 3)))})
+    cx = np.array([-1e8, 0.0, 1e8])
+    write_netcdf3(tmp_path / "current.nc", [("x", 3), ("y", 3)],
+                  {"x": (["x"], cx), "y": (["y"], cx), "u": (["x", "y"], 0.01 * np.ones((3, 3))),
+                   "v": (["x", "y"], 0.01 * np.ones((3, 3)))})
+    return tmp_path / "island.nc", tmp_path / "current.nc"
+
+
+def test_single_ray(gpu, island_and_current):
+    """test_core.py:40-53"""
+    island, current = island_and_current
+    ds = mantaray.single_ray(-1000, 0, 0.01, 0, 10, 2, island, current)
+    assert ds.sizes["time_step"] == 6
+    assert (np.asarray(ds.kx) == 0.01).all()
+    assert (np.asarray(ds.ky) == 0.0).all()
+    np.testing.assert_array_equal(np.asarray(ds.time), [0.0, 2.0, 4.0, 6.0, 8.0, 10.0])
+
+
+def test_multiple_rays(gpu, island_and_current):
+    """test_core.py:56-78"""
+    island, current = island_and_current
+    ds = mantaray.ray_tracing(3 * [-1000], 3 * [0], 3 * [0.01], 3 * [0], 10, 2, str(island), str(current))
+    assert ds.sizes["time_step"] == 6
+    assert ds.sizes["ray"] == 3
+    assert (np.asarray(ds.kx) == 0.01).all()
+    assert (np.asarray(ds.ky) == 0.0).all()
+
+
+def test_rays_variable_length(gpu, oracle, island_and_current):
+    """test_core.py:81-101 (which only runs it); here also checked against the oracle: the Dataset is
+    padded to the longest ray and the shorter ray's tail is NaN, time included."""
+    island, current = island_and_current
+    ds = mantaray.ray_tracing(2 * [-1e3], 2 * [0], [-0.01, 0.01], 2 * [0], 1e6, 20, str(island), str(current))
+    ref = oracle.trace_many(CartesianNetcdf3.open(island), CartesianCurrent.open(current),
+                            2 * [-1e3], 2 * [0], [-0.01, 0.01], 2 * [0], 0.0, 1e6, 20.0)
+    assert ds.sizes["ray"] == 2 and ds.sizes["time_step"] == int(ref.rows.max()) < 50_001
+    short = int(ref.rows.min())
+    x = np.asarray(ds.x)
+    t = np.asarray(ds.time)
+    assert np.isnan(x[short:, 0]).all() and np.isnan(t[short:, 0]).all() and not np.isnan(t[:short, 0]).any()
+    L = ds.sizes["time_step"]
+    np.testing.assert_allclose(x[: short - 1, 0], ref.x[: short - 1, 0], rtol=1e-9)
+    np.testing.assert_allclose(x[: L - 1, 1], ref.x[: L - 1, 1], rtol=1e-9)
+
+
+def test_file_entry_point_matches_descriptor_entry_point(gpu, tmp_path):
+    wl = W.c2_sea_mount(300, 200, half=50)
+    b, c = wl.bathymetry, wl.current
+    write_netcdf3(tmp_path / "b.nc", [("y", b.y.size), ("x", b.x.size)],
+                  {"x": (["x"], b.x), "y": (["y"], b.y), "depth": (["y", "x"], b.depth.reshape(b.y.size, b.x.size))})
+    write_netcdf3(tmp_path / "c.nc", [("y", c.y.size), ("x", c.x.size)],
+                  {"x": (["x"], c.x), "y": (["y"], c.y), "u": (["y", "x"], c.u.reshape(c.y.size, c.x.size)),
+                   "v": (["y", "x"], c.v.reshape(c.y.size, c.x.size))})
+    rays = wl.all_rays()
+    with Fields(b, c) as f1, Fields.open_netcdf3(tmp_path / "b.nc", tmp_path / "c.nc") as f2:
+        r1 = trace_many(f1, *rays, 0.0, wl.duration, wl.dt)
+        r2 = trace_many(f2, *rays, 0.0, wl.duration, wl.dt)
+    for name in ("x", "y", "kx", "ky", "rows", "len"):
+        np.testing.assert_array_equal(getattr(r1, name), getattr(r2, name))
+    # defaults when a path is NULL: ConstantDepth 2000 m / ConstantCurrent (0, 0)
+    with Fields.open_netcdf3(None, None) as f3, Fields(mantaray_b200.ConstantDepth(2000.0), mantaray_b200.ConstantCurrent(0, 0)) as f4:
+        a = trace_many(f3, [0.0], [0.0], [0.05], [0.01], 0.0, 50.0, 1.0)
+        bb = trace_many(f4, [0.0], [0.0], [0.05], [0.01], 0.0, 50.0, 1.0)
+    np.testing.assert_array_equal(a.x, bb.x)
+
+
+def test_file_errors_raise(gpu, tmp_path):
+    with pytest.raises(OSError):
+        mantaray.single_ray(0, 0, 0.01, 0, 10, 2, tmp_path / "nope.nc", tmp_path / "nope2.nc")
+    junk = tmp_path / "junk.nc"
+    junk.write_bytes(b"not a netcdf file at all")
+    with pytest.raises(_capi.MantarayError):
+        Fields.open_netcdf3(junk, None)
+
+
+@pytest.mark.parametrize("spacing", [500.0, 10.0, 25.0, 50.0, 1000.0, 1.0, 0.1, 3.0, 37.3, 41.7, 1e-3, 12345.678, 0.30000001192092896, 7.0e5])
+def test_f32_index_division_is_exact_for_every_float(gpu, spacing):
+    """fdiv_const (Markstein, two exact-residual steps) == IEEE divide for ALL 2^31 non-negative finite floats."""
+    bad = C.c_uint64(123)
+    usable = C.c_int32(-1)
+    rc = _capi.load().mr_selftest_fdiv(0, spacing, C.byref(bad), C.byref(usable))
+    assert rc == 0 and usable.value == 1
+    assert bad.value == 0, f"{bad.value} floats divide differently by {spacing}"
+
+
+def test_division_shortcut_refuses_the_excluded_divisors(gpu):
+    bad, usable = C.c_uint64(0), C.c_int32(-1)
+    all_ones = np.frombuffer(np.uint32(0x3fffffff).tobytes(), dtype=np.float32)[0]      # significand all ones
+    assert _capi.load().mr_selftest_fdiv(0, float(all_ones), C.byref(bad), C.byref(usable)) == 0 and usable.value == 0
+    assert _capi.load().mr_selftest_fdiv(0, 1e-40, C.byref(bad), C.byref(usable)) == 0 and usable.value == 0
+
+
+def test_non_affine_grid_takes_the_general_path_and_agrees(oracle, gpu):
+    """x = f32(i) * 0.1f is NOT exactly affine in f32: the kernel must load the corner coordinates and divide
+    per cell (interpolator.rs:64-72) instead of using launch constants."""
+    n = 300
+    x = (np.arange(n, dtype=np.float32) * np.float32(0.1)).astype(np.float32)
+    assert len(set(np.diff(x.astype(np.float64)))) > 1
+    X, Y = np.meshgrid(x.astype(np.float64), x.astype(np.float64))
+    bathy = CartesianNetcdf3(x, x, 2.0 + 0.5 * np.sin(X) * np.cos(0.7 * Y))
+    cur = CartesianCurrent(x.astype(np.float64), x.astype(np.float64), 0.2 * np.cos(Y), 0.1 * np.sin(X))
+    rng = np.random.default_rng(5)
+    m = 2000
+    th = rng.uniform(0, 2 * np.pi, m)
+    rays = (rng.uniform(1, 28, m), rng.uniform(1, 28, m), 1.5 * np.cos(th), 1.5 * np.sin(th))
+    ref = oracle.trace_many(bathy, cur, *rays, 0.0, 6.0, 0.01)
+    for math in (_abi.MR_MATH_FAST, _abi.MR_MATH_STRICT):
+        with Fields(bathy, cur) as f:
+            res = trace_many(f, *rays, 0.0, 6.0, 0.01, math=math)
+        assert_parity(res, ref, what=f"non-affine math={math}")
+
+
+def test_rays_on_grid_lines_and_nodes(oracle, gpu):
+    """Starts exactly on grid nodes / lines / domain edges: the corner-coincidence early return of
+    interpolator.rs:46-50 and the edge rules of four_corners."""
+    wl = W.c3_shear_jet(16, 40, nx=64)
+    d = 50.0
+    xs = np.array([0.0, d, 2 * d, 10 * d, 63 * d, 63 * d, 5 * d, 5.5 * d, 0.0, 31 * d, 32 * d, 32 * d])
+    ys = np.array([0.0, d, 7.5 * d, 10 * d, 63 * d, 0.0, 5 * d, 5 * d, 63 * d, 20 * d, 20 * d, 20.5 * d])
+    kx = np.array([0.04, 0.04, 0.04, -0.04, -0.04, -0.03, 0.0, 0.04, 0.03, 0.04, 0.04, -0.04])
+    ky = np.array([0.01, 0.0, 0.0, 0.0, -0.01, 0.02, 0.04, 0.0, -0.02, 0.0, 0.0, 0.0])
+    ref = oracle.trace_many(wl.bathymetry, wl.current, xs, ys, kx, ky, 0.0, 40.0, 1.0)
+    for math in (_abi.MR_MATH_FAST, _abi.MR_MATH_STRICT):
+        with Fields(wl.bathymetry, wl.current) as f:
+            res = trace_many(f, xs, ys, kx, ky, 0.0, 40.0, 1.0, math=math)
+        assert_parity(res, ref, what=f"grid lines math={math}")
+
+
+def test_multi_device_handle_shards_and_gathers(gpu):
+    """Rays split in contiguous blocks over the devices of the handle; the gather is a concatenation."""
+    ndev = _capi.device_count()
+    if ndev < 2:
+        pytest.skip("one visible device")
+    wl = W.c4_agulhas(40, 40, 200)
+    rays = wl.all_rays()
+    with Fields(wl.bathymetry, wl.current, devices=[0]) as f1, Fields(wl.bathymetry, wl.current, devices=list(range(ndev))) as fn:
+        assert fn.device_mask == (1 << ndev) - 1
+        a = trace_many(f1, *rays, 0.0, wl.duration, wl.dt, final_state=True)
+        b = trace_many(fn, *rays, 0.0, wl.duration, wl.dt, final_state=True)
+    for name in ("t", "x", "y", "kx", "ky", "rows", "len", "final_state"):
+        np.testing.assert_array_equal(getattr(a, name), getattr(b, name), err_msg=name)

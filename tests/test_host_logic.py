@@ -1,0 +1,122 @@
+"""Host-side logic that needs no GPU: Dataset assembly (python/mantaray/core.py:114-132), the
+RayBundle sequence view of `Vec<Vec<(t,x,y,kx,ky)>>`, workload sharding, and the N>1 bench
+reduction logic over gloo."""
+
+import os
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+import pytest
+
+from mantaray_b200 import _capi, _mantaray, core
+from mantaray_b200 import workloads as W
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def fake_result():
+    nan = np.nan
+    t = np.array([0.0, 2.0, 4.0, 6.0])
+    x = np.array([[1.0, 10.0, 100.0], [2.0, 20.0, 200.0], [3.0, nan, 300.0], [nan, nan, nan]])
+    rows = np.array([4, 3, 3], dtype=np.int32)          # ray 2 ran out of steps... ray 0 stopped on a NaN row
+    ln = np.array([3, 2, 3], dtype=np.int32)
+    return _capi.TraceResult(t, x, x + 0.5, x * 0 + 0.01, x * 0, rows, ln, None, 1)
+
+
+def test_ray_bundle_is_a_sequence_of_per_ray_rows():
+    b = _mantaray.RayBundle(fake_result())
+    assert len(b) == 3
+    assert [r.shape for r in b] == [(4, 5), (3, 5), (3, 5)]
+    np.testing.assert_array_equal(b[1][:, 0], [0.0, 2.0, 4.0])
+    np.testing.assert_array_equal(b[1][:2, 1], [10.0, 20.0])
+    assert np.isnan(b[0][3, 1:]).all() and b[0][3, 0] == 6.0     # trailing NaN row keeps its time
+    with pytest.raises(IndexError):
+        b[3]
+
+
+def test_ray_tracing_dataset_assembly(monkeypatch):
+    """NaN-pad to the LONGEST ray (not to S+1), dims (time_step, ray), time NaN beyond a ray's rows."""
+    res = fake_result()
+    big = _capi.TraceResult(np.arange(6) * 2.0, *(np.vstack([a, np.full((2, 3), np.nan)]) for a in (res.x, res.y, res.kx, res.ky)),
+                            res.rows, res.len, None, 1)
+    monkeypatch.setattr(_mantaray, "ray_tracing", lambda *a: _mantaray.RayBundle(big))
+    ds = core.ray_tracing([0] * 3, [0] * 3, [0] * 3, [0] * 3, 10.0, 2.0, "b.nc", "c.nc")
+    assert dict(ds.sizes) == {"time_step": 4, "ray": 3}
+    np.testing.assert_array_equal(np.asarray(ds["time"])[:, 0], [0.0, 2.0, 4.0, 6.0])
+    np.testing.assert_array_equal(np.asarray(ds["time"])[:, 1], [0.0, 2.0, 4.0, np.nan])
+    np.testing.assert_array_equal(np.asarray(ds["x"]), res.x)
+    assert list(np.asarray(ds["time_step"])) == [0, 1, 2, 3] and list(np.asarray(ds["ray"])) == [0, 1, 2]
+    assert "date_created" in ds.attrs
+    assert (np.asarray(ds.kx)[~np.isnan(np.asarray(ds.kx))] == 0.01).all()
+
+
+def test_single_ray_dataset_assembly(monkeypatch):
+    rows = np.array([[0.0, 1.0, 2.0, 0.01, 0.0], [2.0, 3.0, 4.0, 0.01, 0.0]])
+    monkeypatch.setattr(_mantaray, "single_ray", lambda *a: rows)
+    ds = core.single_ray(0, 0, 0.01, 0, 2.0, 2.0, "b.nc", "c.nc")
+    assert dict(ds.sizes) == {"time_step": 2}
+    np.testing.assert_array_equal(np.asarray(ds["x"]), [1.0, 3.0])
+    assert (np.asarray(ds.kx) == 0.01).all() and (np.asarray(ds.ky) == 0.0).all()
+
+
+def test_shard_ranges_partition_the_rays():
+    for n, world in [(1_000_000, 8), (1000, 3), (5, 8), (128, 2), (67_108_864, 8)]:
+        spans = [W.shard_range(n, r, world) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))        # contiguous, in input order
+        assert all(lo % 128 == 0 for lo, hi in spans if lo < n)           # whole thread blocks
+    wl = W.c4_agulhas(4, 8, 16, nx=64)
+    whole = np.stack(wl.all_rays())
+    parts = np.concatenate([np.stack(wl.rays(*W.shard_range(wl.n_rays, r, 3, align=4))) for r in range(3)], axis=1)
+    np.testing.assert_array_equal(whole, parts)                           # a rank builds exactly its block
+
+
+def test_workload_shapes():
+    for name, wl in [("C1", W.c1_canonical(10, 10)), ("C2", W.c2_sea_mount(10, 10, half=20)), ("C3", W.c3_shear_jet(10, 10, nx=32)),
+                     ("C4", W.c4_agulhas(3, 3, 10, nx=32)), ("C5", W.c5_nazare(2, 2, 3, 10, nx=32, stride=5))]:
+        x0, y0, kx0, ky0 = wl.all_rays()
+        assert x0.shape == y0.shape == kx0.shape == ky0.shape == (wl.n_rays,)
+        assert wl.bathymetry.x.dtype == np.float32 and wl.current.x.dtype == np.float64
+        assert wl.n_steps == 10 and wl.n_rows == 10 // wl.stride + 1, name
+
+
+GLOO_SCRIPT = textwrap.dedent("""
+    import os, sys, json
+    import numpy as np, torch, torch.distributed as dist
+    sys.path.insert(0, %r)
+    from mantaray_b200 import workloads as W
+    from oracle import mr_oracle as O
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    wl = W.c2_sea_mount(512, 120, half=60)      # 2 x 256: equal shards (gloo all_gather needs equal sizes)
+    lo, hi = W.shard_range(wl.n_rays, rank, world)
+    r = O.trace_many(wl.bathymetry, wl.current, *wl.rays(lo, hi), 0.0, wl.duration, wl.dt, nthreads=1)
+    # what bench.py reduces: executed ray-steps (SUM) and elapsed time (MAX)
+    e = torch.tensor([float((r.rows - 1).sum())], dtype=torch.float64); dist.all_reduce(e, op=dist.ReduceOp.SUM)
+    t = torch.tensor([1.0 + rank], dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    # and the gather is a concatenation along `ray`
+    rows = [torch.zeros(W.shard_range(wl.n_rays, k, world)[1] - W.shard_range(wl.n_rays, k, world)[0], dtype=torch.int32) for k in range(world)]
+    dist.all_gather(rows, torch.from_numpy(r.rows.copy()))
+    if rank == 0:
+        full = O.trace_many(wl.bathymetry, wl.current, *wl.all_rays(), 0.0, wl.duration, wl.dt, nthreads=1)
+        ok = bool((torch.cat(rows).numpy() == full.rows).all())
+        print(json.dumps({"E": e.item(), "E_full": float((full.rows - 1).sum()), "tmax": t.item(), "concat_ok": ok}))
+    dist.destroy_process_group()
+""")
+
+
+def test_two_rank_sharding_over_gloo(tmp_path):
+    """world_size 2 on CPU: per-rank shards cover the batch, SUM/MAX reductions as bench.py does them."""
+    script = tmp_path / "gloo_shard.py"
+    script.write_text(GLOO_SCRIPT % ROOT)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29617", str(script)],
+                         capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    import json
+    line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
+    r = json.loads(line)
+    assert r["E"] == r["E_full"] and r["tmax"] == 2.0 and r["concat_ok"]

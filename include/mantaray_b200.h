@@ -259,8 +259,11 @@ int  mr_measure_fp64_peak(int device, int millis, double *tflops);
 /* Self-test of the fast path's exact f32 division by a launch constant (the fractional
  * index of src/bathymetry/cartesian_netcdf3.rs:289): compares it with the IEEE divide for
  * EVERY non-negative finite float t, for the divisor `spacing`, on `device`.  *mismatches
- * receives the number of t whose quotients differ in any bit (NaN/inf classes compared as
- * classes); *usable receives 0 if the library would not use the shortcut for this spacing. */
+ * receives the number of t whose quotients differ in any bit, except that an infinite
+ * quotient may come out as NaN (both are out of bounds) and that for 0 < t < 2^-100 (where
+ * the exact residual underflows) both quotients only have to lie in [0, 1), i.e. cell 0 and in
+ * bounds either way; *usable receives 0 if the library would not use the shortcut for this
+ * spacing. */
 int  mr_selftest_fdiv(int device, float spacing, uint64_t *mismatches, int32_t *usable);
 
 #ifdef __cplusplus

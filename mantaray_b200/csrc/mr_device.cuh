@@ -160,8 +160,10 @@ __device__ __forceinline__ float corner_pick(float r, bool at_xa, bool at_xb, bo
 // host): q0 = RN(t r) is within 2 ulp; one exact-residual step makes it faithful, a second
 // makes it the correctly rounded quotient (Markstein 1990; the host falls back to the true
 // divide if s has an all-ones significand, the theorem's exception).  Verified exhaustively
-// against __fdiv_rn over every float for a set of spacings by tests/test_gpu_division.py.
-// +-inf gives NaN instead of +-inf; both are out of bounds for the caller.
+// against __fdiv_rn over every float for a set of spacings by tests/test_gpu_api.py
+// (mr_selftest_fdiv): bit-identical for every |t| >= 2^-100; below that the exact residual
+// underflows and the last bits can differ, but both quotients are in [0, 1) (s > 1e-30), i.e.
+// cell 0 and in bounds either way.  +-inf gives NaN instead of +-inf; both are out of bounds.
 __device__ __forceinline__ float fdiv_const(float t, float s, float r)
 {
     float q = __fmul_rn(t, r);

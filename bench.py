@@ -301,6 +301,7 @@ def main():
     ms_total = allmax(ms_total)
     clocks = sampler.summary(t_lo, t_hi) if sampler else None
     value = E * args.steps / (ms_total * 1e-3)
+    n_launch_total = int(allsum(float(n_launch)))          # trace kernels launched in the timed region, all ranks
     kernel_ms = float(np.mean(ms_each))           # one kernel per step: its average launch duration
 
     # ---- roofline of the dominant (only) kernel ----------------------------------------
@@ -405,7 +406,7 @@ def main():
                     wl.bathymetry.depth.nbytes * 3 / 1e6),
             },
             "roofline": roofline, "roofline_hbm": roofline_hbm,
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": n_launch, "clocks": clocks,
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": n_launch_total, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
     fields.free()

@@ -177,7 +177,7 @@ __global__ void build_bathy_cells(const double *depth, int nx, int ny, double x_
         const size_t x1 = i % (size_t)(nx - 1), y1 = i / (size_t)(nx - 1);
         const double *p = depth + (size_t)nx * y1 + x1;
         const double sw = p[0], se = p[1], nw = p[nx], ne = p[nx + 1];
-        cell[2 * i] = make_float4((float)sw, (float)nw, (float)ne, (float)se);
+        cell[2 * i] = bilinear_coeffs((float)sw, (float)nw, (float)ne, (float)se);
         // `as f32` (cartesian_netcdf3.rs:134) then `as f64` (wave_ray_path.rs:125-126)
         const double gx = (double)(float)__ddiv_rn(__dsub_rn(se, sw), x_space);
         const double gy = (double)(float)__ddiv_rn(__dsub_rn(nw, sw), y_space);
@@ -194,8 +194,8 @@ __global__ void build_current_cells(const double *u, const double *v, int nx, in
         const double *pu = u + (size_t)nx * y1 + x1, *pv = v + (size_t)nx * y1 + x1;
         const double usw = pu[0], use_ = pu[1], unw = pu[nx], une = pu[nx + 1];
         const double vsw = pv[0], vse = pv[1], vnw = pv[nx], vne = pv[nx + 1];
-        cell_uv[2 * i] = make_float4((float)usw, (float)unw, (float)une, (float)use_);
-        cell_uv[2 * i + 1] = make_float4((float)vsw, (float)vnw, (float)vne, (float)vse);
+        cell_uv[2 * i] = bilinear_coeffs((float)usw, (float)unw, (float)une, (float)use_);
+        cell_uv[2 * i + 1] = bilinear_coeffs((float)vsw, (float)vnw, (float)vne, (float)vse);
         cell_grad[2 * i] = make_double2(__ddiv_rn(__dsub_rn(use_, usw), x_space), __ddiv_rn(__dsub_rn(unw, usw), y_space));
         cell_grad[2 * i + 1] = make_double2(__ddiv_rn(__dsub_rn(vse, vsw), x_space), __ddiv_rn(__dsub_rn(vnw, vsw), y_space));
     }

@@ -44,7 +44,7 @@ struct BathyDev {
     float  rsx, rsy;           // RN(1/sx), RN(1/sy); 0 when the exact-division shortcut does not apply
     double x_space, y_space;   // x[1]-x[0] in f64 of the f32 values (cartesian_netcdf3.rs:119-120)
     // per-cell records for the fast path: cell (x1,y1), x1 < nx-1, y1 < ny-1, 32 bytes each:
-    //   float4 {z_sw, z_nw, z_ne, z_se} (depth as f32), double2 {dhdx, dhdy} (the f32 gradient of
+    //   float4 {z_sw, a10, a01, a11} (bilinear_coeffs of the corner depths as f32), double2 {dhdx, dhdy} (the f32 gradient of
     //   cartesian_netcdf3.rs:134, stored already widened back to f64 as wave_ray_path.rs:125-126 does)
     const float4 *cell;
     float nxm1f, nym1f;        // (nx-1) as f32, (ny-1) as f32: the bound of cartesian_netcdf3.rs:291
@@ -64,7 +64,7 @@ struct CurrentDev {
     double sx, sy;             // |x[1]-x[0]|, |y[1]-y[0]|          (cartesian_current.rs:244)
     double inv_sx, inv_sy;     // RN(1/sx), RN(1/sy)
     double x_space, y_space;   // x[1]-x[0] (signed)                (cartesian_current.rs:515-516)
-    // fast path: per cell two float4 {u_sw,u_nw,u_ne,u_se}, {v_sw,v_nw,v_ne,v_se} (as f32) and
+    // fast path: per cell two float4 bilinear_coeffs of the u and of the v corners (as f32) and
     // two double2 {dudx,dudy}, {dvdx,dvdy} (the f64 finite differences, already divided)
     const float4  *cell_uv;
     const double2 *cell_grad;
@@ -133,22 +133,31 @@ __device__ __forceinline__ bool bilinear_cell_strict(float xa, float xb, float y
     return true;
 }
 
-// fast form.  The cell's fractional coordinates (X, Y) are resolved once per lookup and
-// shared by every variable interpolated on that cell.
-__device__ __forceinline__ float bilinear_xy(float X, float Y, float zsw, float znw, float zne, float zse)
+// fast form.  The cell's fractional coordinates (X, Y) are resolved once per lookup and shared by
+// every variable interpolated on that cell; the corner combinations a10 = z_nw - z_sw,
+// a01 = z_se - z_sw, a11 = ((z_ne - z_sw) - a10) - a01 of interpolator.rs:78-81 depend on the cell
+// only and are part of its record (computed once at upload with these same f32 operations).
+__device__ __forceinline__ float4 bilinear_coeffs(float zsw, float znw, float zne, float zse)
 {
-    float a10 = __fsub_rn(znw, zsw);
-    float a01 = __fsub_rn(zse, zsw);
-    float a11 = __fsub_rn(__fsub_rn(__fsub_rn(zne, zsw), a10), a01);
-    float r = __fadd_rn(zsw, __fmul_rn(a10, X));
-    r = __fadd_rn(r, __fmul_rn(a01, Y));
-    return __fadd_rn(r, __fmul_rn(__fmul_rn(a11, X), Y));
+    const float a10 = __fsub_rn(znw, zsw);
+    const float a01 = __fsub_rn(zse, zsw);
+    const float a11 = __fsub_rn(__fsub_rn(__fsub_rn(zne, zsw), a10), a01);
+    return make_float4(zsw, a10, a01, a11);
+}
+__device__ __forceinline__ float bilinear_xy(float X, float Y, const float4 &c)    // interpolator.rs:83
+{
+    float r = __fadd_rn(c.x, __fmul_rn(c.y, X));
+    r = __fadd_rn(r, __fmul_rn(c.z, Y));
+    return __fadd_rn(r, __fmul_rn(__fmul_rn(c.w, X), Y));
 }
 // interpolator.rs:46-50: a target coincident with a corner returns that corner's value, tested in
-// the order a, b, c, d (the later selects below take precedence).
+// the order a, b, c, d (the later selects below take precedence).  Rare; the raw corner values
+// are re-read from the f64 node grid.
 __device__ __forceinline__ float corner_pick(float r, bool at_xa, bool at_xb, bool at_ya, bool at_yb,
-                                             float zsw, float znw, float zne, float zse)
+                                             const double *node, int nx)
 {
+    const float zsw = (float)__ldg(node), zse = (float)__ldg(node + 1);
+    const float znw = (float)__ldg(node + nx), zne = (float)__ldg(node + nx + 1);
     r = (at_xb && at_ya) ? zse : r;
     r = (at_xb && at_yb) ? zne : r;
     r = (at_xa && at_yb) ? znw : r;
@@ -300,47 +309,6 @@ __device__ __forceinline__ bool current_grid_strict(const CurrentDev &c, double 
     o.dvdx = __ddiv_rn(__dsub_rn(vse, vsw), c.x_space);
     o.dvdy = __ddiv_rn(__dsub_rn(vnw, vsw), c.y_space);
     return true;
-}
-
-// =============================================================================
-// look-ahead prefetch of the per-cell records
-// =============================================================================
-// A ray enters a new cell roughly once per step (dt ~ dd/cg, the reference's own CFL
-// convention), so the first lookup in a cell is a compulsory L1 miss and, with one ray per
-// thread, every warp waits for its slowest lane.  After stage 0 the kernel knows k0; the
-// records under y + 2 dt k0 (the far end of the NEXT step) are requested now and arrive
-// while the remaining three stages run.  Approximate arithmetic is enough here: a wrong
-// guess only costs the miss it failed to hide.
-#ifndef MR_PREFETCH
-#define MR_PREFETCH 0          // 0 off, 1 prefetch.global.L1, 2 prefetch.global.L2
-#endif
-__device__ __forceinline__ void prefetch_line(const void *p)
-{
-#if MR_PREFETCH == 1
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-#elif MR_PREFETCH == 2
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-#else
-    (void)p;
-#endif
-}
-
-template <int BK, int CK>
-__device__ __forceinline__ void prefetch_cells(const BathyDev &b, const CurrentDev &c, double xp, double yp)
-{
-#if MR_PREFETCH
-    const float xf = (float)xp, yf = (float)yp;
-    if (BK == MR_BATHY_GRID) {
-        const int x1 = cell_of(__fdividef(xf - b.xf0, b.sx), b.nx), y1 = cell_of(__fdividef(yf - b.yf0, b.sy), b.ny);
-        prefetch_line(b.cell + 2 * ((size_t)(b.nx - 1) * y1 + x1));
-    }
-    if (CK == MR_CURRENT_GRID) {
-        const int x1 = cell_of(__fdividef(xf - c.xf0, (float)c.sx), c.nx), y1 = cell_of(__fdividef(yf - c.yf0, (float)c.sy), c.ny);
-        const size_t cell = (size_t)(c.nx - 1) * y1 + x1;
-        prefetch_line(c.cell_uv + 2 * cell);
-        prefetch_line(c.cell_grad + 2 * cell);
-    }
-#endif
 }
 
 // =============================================================================
@@ -566,10 +534,11 @@ __device__ __forceinline__ void rhs_fast(const BathyDev &b, const CurrentDev &c,
             c01 = -__fdiv_rn(dx, det); c10 = -__fdiv_rn(dy, det);              // :70-71
         }
         const float X = __fmul_rn(c01, __fsub_rn(yf, bya)), Y = __fmul_rn(c10, __fsub_rn(xf, bxa));
-        h32 = bilinear_xy(X, Y, Z.x, Z.y, Z.z, Z.w);
+        h32 = bilinear_xy(X, Y, Z);
         if (xf == bxa || xf == bxb) {
             const bool at_ya = yf == bya, at_yb = yf == byb;
-            if (at_ya || at_yb) h32 = corner_pick(h32, xf == bxa, xf == bxb, at_ya, at_yb, Z.x, Z.y, Z.z, Z.w);
+            if (at_ya || at_yb)
+                h32 = corner_pick(h32, xf == bxa, xf == bxb, at_ya, at_yb, b.depth + (size_t)b.nx * by1 + bx1, b.nx);
         }
         dhdx = gh.x; dhdy = gh.y;
     } else {
@@ -590,13 +559,14 @@ __device__ __forceinline__ void rhs_fast(const BathyDev &b, const CurrentDev &c,
             c01 = -__fdiv_rn(dx, det); c10 = -__fdiv_rn(dy, det);
         }
         const float X = __fmul_rn(c01, __fsub_rn(yf, cya)), Y = __fmul_rn(c10, __fsub_rn(xf, cxa));
-        float u32 = bilinear_xy(X, Y, U.x, U.y, U.z, U.w);
-        float v32 = bilinear_xy(X, Y, V.x, V.y, V.z, V.w);
+        float u32 = bilinear_xy(X, Y, U);
+        float v32 = bilinear_xy(X, Y, V);
         if (xf == cxa || xf == cxb) {
             const bool at_ya = yf == cya, at_yb = yf == cyb;
             if (at_ya || at_yb) {
-                u32 = corner_pick(u32, xf == cxa, xf == cxb, at_ya, at_yb, U.x, U.y, U.z, U.w);
-                v32 = corner_pick(v32, xf == cxa, xf == cxb, at_ya, at_yb, V.x, V.y, V.z, V.w);
+                const size_t node = (size_t)c.nx * cy1 + cx1;
+                u32 = corner_pick(u32, xf == cxa, xf == cxb, at_ya, at_yb, c.u + node, c.nx);
+                v32 = corner_pick(v32, xf == cxa, xf == cxb, at_ya, at_yb, c.v + node, c.nx);
             }
         }
         cv.u = (double)u32; cv.v = (double)v32;

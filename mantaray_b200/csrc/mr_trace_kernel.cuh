@@ -50,6 +50,9 @@ static constexpr int kBlock = 128;
 #ifndef MR_MIN_BLOCKS
 #define MR_MIN_BLOCKS 7
 #endif
+#ifndef MR_STREAM_STORES
+#define MR_STREAM_STORES 1
+#endif
 static constexpr int kStageUnroll = MR_STAGE_UNROLL;
 
 __device__ __forceinline__ bool any_nan4(const double y[4])
@@ -143,7 +146,11 @@ trace_kernel(const __grid_constant__ TraceArgs a)
             o += a.ld;
             --rows_left;
             if (store) {
+#if MR_STREAM_STORES
+                __stcs(a.x + o, y[0]); __stcs(a.y + o, y[1]); __stcs(a.kx + o, y[2]); __stcs(a.ky + o, y[3]);
+#else
                 a.x[o] = y[0]; a.y[o] = y[1]; a.kx[o] = y[2]; a.ky[o] = y[3];
+#endif
             }
         }
     }

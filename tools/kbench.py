@@ -22,6 +22,12 @@ def child(lib_path, rays, steps, workload, math, notraj=False, nx=2048):
           "C3": lambda: W.c3_shear_jet(rays, steps), "C5": lambda: W.c5_nazare(8, 8, rays // 64, steps)}[workload]()
     x0, y0, kx0, ky0 = wl.all_rays()
     n = x0.size
+    if os.environ.get("KB_ANALYTIC"):      # same rays, analytic fields: no record loads at all
+        from mantaray_b200 import ConstantDepth, ConstantCurrent, ConstantSlope
+        mode = os.environ["KB_ANALYTIC"]
+        wl.bathymetry = ConstantDepth(4000.0) if mode in ("deep", "deepcur") else ConstantSlope(300.0, 0.0, 0.0, -1e-4, -1e-4)
+        if mode in ("deep", "slope"):
+            wl.current = ConstantCurrent(0.1, -0.05)
     dev = torch.device("cuda", 0)
     f = _capi.Fields(wl.bathymetry, wl.current, devices=[0])
     ic = torch.from_numpy(np.stack([x0, y0, kx0, ky0])).to(dev)

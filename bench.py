@@ -320,17 +320,25 @@ def main():
     alg_flop = E_local * wl.flop_per_ray_step
     ach_tf = alg_flop / (kernel_ms * 1e-3) / 1e12
     ach_gbs = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    traffic = None                                  # DRAM bytes of one launch, from the committed ncu capture
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1", "traffic.json")) as f:
+            tr = json.load(f).get(wl.name)
+        if tr and tr["rays_per_gpu"] == n and tr["rk4_steps"] == wl.n_steps and args.math == "fast":
+            traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+    except Exception:
+        pass
     roofline = {
         "bound": "fp64", "kernel": "mr::trace_kernel<GRID,GRID,%s>" % args.math,
         "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_tf / fp64_peak if fp64_peak else None,
-        "traffic": None,
+        "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read+write); algorithmic bytes per launch = %d" % int(alg_bytes),
         "flop_per_ray_step": wl.flop_per_ray_step,
         "peak_source": "DFMA probe kernel timed in this run (mr_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
         "kernel_ms": kernel_ms,
     }
     roofline_hbm = {
         "bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
-        "traffic": None, "bytes_per_stored_row": W.BYTES_PER_ROW, "peak_source": hbm_src,
+        "traffic": traffic, "algorithmic_bytes": int(alg_bytes), "bytes_per_stored_row": W.BYTES_PER_ROW, "peak_source": hbm_src,
     }
 
     # ---- end to end through the C ABI with host buffers ---------------------------------
@@ -341,7 +349,7 @@ def main():
         avail = psutil.virtual_memory().available
         local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
         per_ray = 32.0 * rows_cap if full else 0.0
-        budget = min(0.25 * avail / max(local_world, 1), 24e9)
+        budget = min(0.30 * avail / max(local_world, 1), 70e9)
         n_e2e = n if per_ray == 0 else int(min(n, max(budget // per_ray, 1024)))
         n_e2e = max(n_e2e // 128 * 128, min(n, 128))
         sel = slice(0, n_e2e)

@@ -153,7 +153,7 @@ static int validate(const mr_bathymetry_desc *b, const mr_current_desc *c)
     case MR_CURRENT_CONSTANT: break;
     case MR_CURRENT_GRID:
         if (c->nx < 2 || c->ny < 2) return fail(MR_ERR_BAD_ARG, "current grid needs nx >= 2 and ny >= 2");
-        if ((int64_t)(c->nx - 1) * (c->ny - 1) > 0x7fffffffLL) return fail(MR_ERR_BAD_ARG, "current grid has more than 2^31 cells");
+        if ((int64_t)(c->nx - 1) * (c->ny - 1) > 0x3fffffffLL) return fail(MR_ERR_BAD_ARG, "current grid has more than 2^30 cells");
         if (!c->x || !c->y || !c->u || !c->v) return fail(MR_ERR_BAD_ARG, "current grid: NULL x / y / u / v");
         {
             double sx = fabs(c->x[1] - c->x[0]), sy = fabs(c->y[1] - c->y[0]);
@@ -186,7 +186,7 @@ __global__ void build_bathy_cells(const double *depth, int nx, int ny, double x_
 }
 
 __global__ void build_current_cells(const double *u, const double *v, int nx, int ny, double x_space, double y_space,
-                                    float4 *cell_uv, double2 *cell_grad)
+                                    float4 *cell)
 {
     const size_t ncell = (size_t)(nx - 1) * (ny - 1);
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < ncell; i += (size_t)gridDim.x * blockDim.x) {
@@ -194,10 +194,11 @@ __global__ void build_current_cells(const double *u, const double *v, int nx, in
         const double *pu = u + (size_t)nx * y1 + x1, *pv = v + (size_t)nx * y1 + x1;
         const double usw = pu[0], use_ = pu[1], unw = pu[nx], une = pu[nx + 1];
         const double vsw = pv[0], vse = pv[1], vnw = pv[nx], vne = pv[nx + 1];
-        cell_uv[2 * i] = bilinear_coeffs((float)usw, (float)unw, (float)une, (float)use_);
-        cell_uv[2 * i + 1] = bilinear_coeffs((float)vsw, (float)vnw, (float)vne, (float)vse);
-        cell_grad[2 * i] = make_double2(__ddiv_rn(__dsub_rn(use_, usw), x_space), __ddiv_rn(__dsub_rn(unw, usw), y_space));
-        cell_grad[2 * i + 1] = make_double2(__ddiv_rn(__dsub_rn(vse, vsw), x_space), __ddiv_rn(__dsub_rn(vnw, vsw), y_space));
+        cell[4 * i] = bilinear_coeffs((float)usw, (float)unw, (float)une, (float)use_);
+        cell[4 * i + 1] = bilinear_coeffs((float)vsw, (float)vnw, (float)vne, (float)vse);
+        double2 *g = reinterpret_cast<double2 *>(cell + 4 * i + 2);
+        g[0] = make_double2(__ddiv_rn(__dsub_rn(use_, usw), x_space), __ddiv_rn(__dsub_rn(unw, usw), y_space));
+        g[1] = make_double2(__ddiv_rn(__dsub_rn(vse, vsw), x_space), __ddiv_rn(__dsub_rn(vnw, vsw), y_space));
     }
 }
 
@@ -294,16 +295,12 @@ static int upload_fields(DeviceFields &d, const mr_bathymetry_desc *b, const mr_
         C.x_space = c->x[1] - c->x[0];                         // :515
         C.y_space = c->y[1] - c->y[0];                         // :516
         const size_t ncell = (size_t)(c->nx - 1) * (c->ny - 1);
-        float4 *cell_uv = nullptr;
-        double2 *cell_grad = nullptr;
-        if ((rc = device_alloc(d, 2 * ncell, &cell_uv))) return rc;
-        if ((rc = device_alloc(d, 2 * ncell, &cell_grad))) return rc;
-        build_current_cells<<<(unsigned)std::min<size_t>((ncell + 255) / 256, 148 * 16), 256>>>(C.u, C.v, c->nx, c->ny, C.x_space, C.y_space,
-                                                                                               cell_uv, cell_grad);
+        float4 *ccells = nullptr;
+        if ((rc = device_alloc(d, 4 * ncell, &ccells))) return rc;
+        build_current_cells<<<(unsigned)std::min<size_t>((ncell + 255) / 256, 148 * 16), 256>>>(C.u, C.v, c->nx, c->ny, C.x_space, C.y_space, ccells);
         MR_CUDA(cudaGetLastError());
-        C.cell_uv = cell_uv;
+        C.cell = ccells;
         C.nxm1d = (double)(c->nx - 1); C.nym1d = (double)(c->ny - 1);
-        C.cell_grad = cell_grad;
         std::vector<float> xf((size_t)c->nx), yf((size_t)c->ny);   // `as f32`, cartesian_current.rs:375-376
         for (int i = 0; i < c->nx; ++i) xf[(size_t)i] = (float)c->x[i];
         for (int i = 0; i < c->ny; ++i) yf[(size_t)i] = (float)c->y[i];

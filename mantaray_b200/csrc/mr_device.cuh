@@ -64,10 +64,9 @@ struct CurrentDev {
     double sx, sy;             // |x[1]-x[0]|, |y[1]-y[0]|          (cartesian_current.rs:244)
     double inv_sx, inv_sy;     // RN(1/sx), RN(1/sy)
     double x_space, y_space;   // x[1]-x[0] (signed)                (cartesian_current.rs:515-516)
-    // fast path: per cell two float4 bilinear_coeffs of the u and of the v corners (as f32) and
-    // two double2 {dudx,dudy}, {dvdx,dvdy} (the f64 finite differences, already divided)
-    const float4  *cell_uv;
-    const double2 *cell_grad;
+    // fast path: one 64-byte record per cell: float4 bilinear_coeffs of the u corners, float4 of the v
+    // corners (as f32), double2 {dudx,dudy}, double2 {dvdx,dvdy} (the f64 finite differences, divided)
+    const float4 *cell;
     const float *xf, *yf;      // coordinates cast to f32 (cartesian_current.rs:375-376)
     double nxm1d, nym1d;       // (nx-1), (ny-1) as f64: the bound of cartesian_current.rs:248
     int32_t uniform;
@@ -75,6 +74,7 @@ struct CurrentDev {
 };
 
 static constexpr double kG = 9.8;            // src/wave_ray_path.rs:23
+static constexpr int kBlockThreads = 128;    // threads per block of the trace kernel
 
 // Taylor coefficients 1/13! .. 1/2! of expm1 (see exp_expm1_neg).  In constant memory so
 // that each DFMA reads its coefficient as a c[bank][offset] operand instead of the
@@ -201,6 +201,24 @@ __device__ __forceinline__ double2 ldg_d2(const double2 *p)
     double2 v;
     asm volatile("ld.global.nc.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
     return v;
+}
+// One 32-byte record in ONE instruction (sm_100 LDG.256): a float4 followed by a double2, or
+// two float4, or two double2.  What arrives together cannot be split into two round trips.
+__device__ __forceinline__ void ldg_f4_d2(const float4 *p, float4 &a, double2 &b)
+{
+    unsigned long long q0, q1;
+    asm volatile("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(q0), "=l"(q1), "=d"(b.x), "=d"(b.y) : "l"(p));
+    a.x = __uint_as_float((unsigned)q0); a.y = __uint_as_float((unsigned)(q0 >> 32));
+    a.z = __uint_as_float((unsigned)q1); a.w = __uint_as_float((unsigned)(q1 >> 32));
+}
+__device__ __forceinline__ void ldg_f4_f4(const float4 *p, float4 &a, float4 &b)
+{
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+}
+__device__ __forceinline__ void ldg_d2_d2(const double2 *p, double2 &a, double2 &b)
+{
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a.x), "=d"(a.y), "=d"(b.x), "=d"(b.y) : "l"(p));
 }
 
 // The cell rule of four_corners (cartesian_netcdf3.rs:344-387, cartesian_current.rs
@@ -497,18 +515,15 @@ __device__ __forceinline__ void rhs_fast(const BathyDev &b, const CurrentDev &c,
     double2 gh = make_double2(0.0, 0.0), gu = gh, gv = gh;
     float bxa = 0.f, bxb = 0.f, bya = 0.f, byb = 0.f, cxa = 0.f, cxb = 0.f, cya = 0.f, cyb = 0.f;
     if (BK == MR_BATHY_GRID) {
-        Z = ldg_f4(brec);
-        gh = ldg_d2((const double2 *)(brec + 1));
+        ldg_f4_d2(brec, Z, gh);
         if (!UNI) {
             bxa = __ldg(b.x + bx1); bxb = __ldg(b.x + bx1 + 1);
             bya = __ldg(b.y + by1); byb = __ldg(b.y + by1 + 1);
         }
     }
     if (CK == MR_CURRENT_GRID) {
-        U = ldg_f4(c.cell_uv + 2u * ccell);
-        V = ldg_f4(c.cell_uv + 2u * ccell + 1);
-        gu = ldg_d2(c.cell_grad + 2u * ccell);
-        gv = ldg_d2(c.cell_grad + 2u * ccell + 1);
+        ldg_f4_f4(c.cell + 4u * ccell, U, V);
+        ldg_d2_d2((const double2 *)(c.cell + 4u * ccell + 2), gu, gv);
         if (!UNI) {
             cxa = __ldg(c.xf + cx1); cxb = __ldg(c.xf + cx1 + 1);
             cya = __ldg(c.yf + cy1); cyb = __ldg(c.yf + cy1 + 1);

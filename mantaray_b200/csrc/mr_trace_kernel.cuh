@@ -40,7 +40,7 @@ struct TraceArgs {
     double *fin;               // [4][n] or NULL
 };
 
-static constexpr int kBlock = 128;
+static constexpr int kBlock = kBlockThreads;
 
 // build-time tuning knobs (see profiles/): unroll factor of the RK4 stage loop and the
 // resident-blocks-per-SM target of the fast kernel

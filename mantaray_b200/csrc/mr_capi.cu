@@ -274,6 +274,7 @@ static int upload_fields(DeviceFields &d, const mr_bathymetry_desc *b, const mr_
         MR_CUDA(cudaGetLastError());
         B.cell = cell;
         B.nxm1f = (float)(b->nx - 1); B.nym1f = (float)(b->ny - 1);
+        B.zero = 0;
         B.uniform = affine_f32(b->x, b->nx, &B.dxf) && affine_f32(b->y, b->ny, &B.dyf) &&
                     basis_coeffs(B.dxf, B.dyf, &B.c01, &B.c10) && recip_ok(B.sx, &B.rsx) && recip_ok(B.sy, &B.rsy);
     } else if (b->kind == MR_BATHY_ARRAY) {

@@ -48,6 +48,7 @@ struct BathyDev {
     //   cartesian_netcdf3.rs:134, stored already widened back to f64 as wave_ray_path.rs:125-126 does)
     const float4 *cell;
     float nxm1f, nym1f;        // (nx-1) as f32, (ny-1) as f32: the bound of cartesian_netcdf3.rs:291
+    int32_t zero;              // always 0, but opaque to the compiler (see rhs_fast, phase 4)
     // coordinates exactly affine in f32 (x[i] == fmaf(i, dxf, x[0]) for every i, same for y):
     // corner coordinates and the change-of-basis coefficients become launch constants
     int32_t uniform;
@@ -511,9 +512,10 @@ __device__ __forceinline__ void rhs_fast(const BathyDev &b, const CurrentDev &c,
         ccell = (unsigned)((c.nx - 1) * cy1 + cx1);
     }
     // ---- phase 2 ---------------------------------------------------------------------
-    float4 Z = make_float4(0.f, 0.f, 0.f, 0.f), U = Z, V = Z;
-    double2 gh = make_double2(0.0, 0.0), gu = gh, gv = gh;
-    float bxa = 0.f, bxb = 0.f, bya = 0.f, byb = 0.f, cxa = 0.f, cxb = 0.f, cya = 0.f, cyb = 0.f;
+    // (only the kinds selected by the template parameters read these; no default initialisation)
+    float4 Z, U, V;
+    double2 gh, gu, gv;
+    float bxa, bxb, bya, byb, cxa, cxb, cya, cyb;
     if (BK == MR_BATHY_GRID) {
         ldg_f4_d2(brec, Z, gh);
         if (!UNI) {
@@ -535,6 +537,13 @@ __device__ __forceinline__ void rhs_fast(const BathyDev &b, const CurrentDev &c,
     sqrt_rsqrt(k2, k, rk);
     const double cs = kx * rk, sn = ky * rk;
     // ---- phase 4 ---------------------------------------------------------------------
+    // Scheduling fence.  ptxas places the first consumer of the bathymetry record ahead of the
+    // current record's loads (whose f64 address chain is longer), so a warp waited for one L2
+    // round trip, issued the other loads, and waited again (profiles/r1/g_*).  OR-ing in
+    // (bits of the current record) & 0 — a zero the compiler cannot see — changes no value but
+    // makes the first bathymetry consumer depend on both loads, so both are in flight first.
+    if (BK == MR_BATHY_GRID && CK == MR_CURRENT_GRID)
+        Z.x = __int_as_float(__float_as_int(Z.x) | (__float_as_int(U.x) & b.zero));
     float h32;
     double dhdx, dhdy;
     if (BK == MR_BATHY_GRID) {

@@ -475,160 +475,198 @@ __device__ __forceinline__ void rhs_f64_fast(double kx, double ky, double k, dou
 // A NaN position needs no special case either: the reference's Ok(NaN depth) also ends in four
 // NaNs (cg and the bathymetric term are NaN), and a NaN index fails the bounds test here.
 // =============================================================================
+// One ray's evaluation in flight.  The four phases are separate functions so that a thread that
+// carries NR rays runs each phase for all of them before the next (rhs_fast_n): the compiler then
+// has NR independent instruction streams to interleave, and the uniform work of a phase (constant
+// loads, loop control) is paid once per thread instead of once per ray.
 template <int BK, int CK, bool UNI>
-__device__ __forceinline__ void rhs_fast(const BathyDev &b, const CurrentDev &c,
-                                         double x, double y, double kx, double ky,
-                                         float xf, float yf, double out[4])
-{
-    // ---- phase 1 ---------------------------------------------------------------------
-    bool ok = true;
-    int bx1 = 0, by1 = 0, cx1 = 0, cy1 = 0;
-    const float4 *brec = nullptr;
-    unsigned ccell = 0;
-    if (BK == MR_BATHY_GRID) {
-        float ix, iy;                                                          // cartesian_netcdf3.rs:289
-        if (UNI) {
-            ix = fdiv_const(__fsub_rn(xf, b.xf0), b.sx, b.rsx);
-            iy = fdiv_const(__fsub_rn(yf, b.yf0), b.sy, b.rsy);
-        } else {
-            ix = __fdiv_rn(__fsub_rn(xf, b.xf0), b.sx);
-            iy = __fdiv_rn(__fsub_rn(yf, b.yf0), b.sy);
-        }
-        ok = ix >= 0.0f && ix <= b.nxm1f && iy >= 0.0f && iy <= b.nym1f;      // :291
-        bx1 = cell_of(ix, b.nx); by1 = cell_of(iy, b.ny);
-        brec = b.cell + 2u * (unsigned)((b.nx - 1) * by1 + bx1);
-    }
-    if (CK == MR_CURRENT_GRID) {
-        // f64 fractional index (cartesian_current.rs:246).  The spacing is a launch constant:
-        // q0 = t*RN(1/s) and one exact-residual correction give the quotient, exactly whenever
-        // t/s is representable (a ray sitting on a grid line), within one ulp otherwise.  An
-        // infinite position turns into NaN here and fails the bounds test like the infinity.
-        const double tx = x - c.xd0, ty = y - c.yd0;
-        const double qx = tx * c.inv_sx, qy = ty * c.inv_sy;
-        const double ix = fma(fma(-qx, c.sx, tx), c.inv_sx, qx);
-        const double iy = fma(fma(-qy, c.sy, ty), c.inv_sy, qy);
-        ok = ok && ix >= 0.0 && ix <= c.nxm1d && iy >= 0.0 && iy <= c.nym1d;  // :248
-        cx1 = cell_of(ix, c.nx); cy1 = cell_of(iy, c.ny);
-        ccell = (unsigned)((c.nx - 1) * cy1 + cx1);
-    }
-    // ---- phase 2 ---------------------------------------------------------------------
-    // (only the kinds selected by the template parameters read these; no default initialisation)
+struct FastRay {
+    float xf, yf;
+    bool ok;
+    int bx1, by1, cx1, cy1;
+    const float4 *brec;
+    unsigned ccell;
+    // (only the kinds selected by the template parameters touch these; no default initialisation)
     float4 Z, U, V;
     double2 gh, gu, gv;
     float bxa, bxb, bya, byb, cxa, cxb, cya, cyb;
-    if (BK == MR_BATHY_GRID) {
-        ldg_f4_d2(brec, Z, gh);
-        if (!UNI) {
-            bxa = __ldg(b.x + bx1); bxb = __ldg(b.x + bx1 + 1);
-            bya = __ldg(b.y + by1); byb = __ldg(b.y + by1 + 1);
+    double k2, k, cs, sn;
+
+    // ---- phase 1: fractional indices and cell addresses ------------------------------------------
+    __device__ __forceinline__ void phase1(const BathyDev &b, const CurrentDev &c, double x, double y)
+    {
+        xf = (float)x; yf = (float)y;                                              // wave_ray_path.rs:122
+        ok = true;
+        if (BK == MR_BATHY_GRID) {
+            float ix, iy;                                                          // cartesian_netcdf3.rs:289
+            if (UNI) {
+                ix = fdiv_const(__fsub_rn(xf, b.xf0), b.sx, b.rsx);
+                iy = fdiv_const(__fsub_rn(yf, b.yf0), b.sy, b.rsy);
+            } else {
+                ix = __fdiv_rn(__fsub_rn(xf, b.xf0), b.sx);
+                iy = __fdiv_rn(__fsub_rn(yf, b.yf0), b.sy);
+            }
+            ok = ix >= 0.0f && ix <= b.nxm1f && iy >= 0.0f && iy <= b.nym1f;      // :291
+            bx1 = cell_of(ix, b.nx); by1 = cell_of(iy, b.ny);
+            brec = b.cell + 2u * (unsigned)((b.nx - 1) * by1 + bx1);
+        }
+        if (CK == MR_CURRENT_GRID) {
+            // f64 fractional index (cartesian_current.rs:246).  The spacing is a launch constant:
+            // q0 = t*RN(1/s) and one exact-residual correction give the quotient, exactly whenever
+            // t/s is representable (a ray sitting on a grid line), within one ulp otherwise.  An
+            // infinite position turns into NaN here and fails the bounds test like the infinity.
+            const double tx = x - c.xd0, ty = y - c.yd0;
+            const double qx = tx * c.inv_sx, qy = ty * c.inv_sy;
+            const double ix = fma(fma(-qx, c.sx, tx), c.inv_sx, qx);
+            const double iy = fma(fma(-qy, c.sy, ty), c.inv_sy, qy);
+            ok = ok && ix >= 0.0 && ix <= c.nxm1d && iy >= 0.0 && iy <= c.nym1d;  // :248
+            cx1 = cell_of(ix, c.nx); cy1 = cell_of(iy, c.ny);
+            ccell = (unsigned)((c.nx - 1) * cy1 + cx1);
         }
     }
-    if (CK == MR_CURRENT_GRID) {
-        ldg_f4_f4(c.cell + 4u * ccell, U, V);
-        ldg_d2_d2((const double2 *)(c.cell + 4u * ccell + 2), gu, gv);
-        if (!UNI) {
-            cxa = __ldg(c.xf + cx1); cxb = __ldg(c.xf + cx1 + 1);
-            cya = __ldg(c.yf + cy1); cyb = __ldg(c.yf + cy1 + 1);
-        }
-    }
-    // ---- phase 3 ---------------------------------------------------------------------
-    const double k2 = fma(kx, kx, ky * ky);
-    double k, rk;
-    sqrt_rsqrt(k2, k, rk);
-    const double cs = kx * rk, sn = ky * rk;
-    // ---- phase 4 ---------------------------------------------------------------------
-    // Scheduling fence.  ptxas places the first consumer of the bathymetry record ahead of the
-    // current record's loads (whose f64 address chain is longer), so a warp waited for one L2
-    // round trip, issued the other loads, and waited again (profiles/r1/g_*).  OR-ing in
-    // (bits of the current record) & 0 — a zero the compiler cannot see — changes no value but
-    // makes the first bathymetry consumer depend on both loads, so both are in flight first.
-    if (BK == MR_BATHY_GRID && CK == MR_CURRENT_GRID)
-        Z.x = __int_as_float(__float_as_int(Z.x) | (__float_as_int(U.x) & b.zero));
-    float h32;
-    double dhdx, dhdy;
-    if (BK == MR_BATHY_GRID) {
-        float c01 = b.c01, c10 = b.c10;
-        if (UNI) {
-            bxa = __fmaf_rn((float)bx1, b.dxf, b.xf0); bxb = __fadd_rn(bxa, b.dxf);
-            bya = __fmaf_rn((float)by1, b.dyf, b.yf0); byb = __fadd_rn(bya, b.dyf);
-        } else {
-            const float dx = __fsub_rn(bxb, bxa), dy = __fsub_rn(byb, bya);
-            const float det = __fsub_rn(0.0f, __fmul_rn(dx, dy));              // interpolator.rs:64
-            ok = ok && det != 0.0f;                                            // :65-67
-            c01 = -__fdiv_rn(dx, det); c10 = -__fdiv_rn(dy, det);              // :70-71
-        }
-        const float X = __fmul_rn(c01, __fsub_rn(yf, bya)), Y = __fmul_rn(c10, __fsub_rn(xf, bxa));
-        h32 = bilinear_xy(X, Y, Z);
-        if (xf == bxa || xf == bxb) {
-            const bool at_ya = yf == bya, at_yb = yf == byb;
-            if (at_ya || at_yb)
-                h32 = corner_pick(h32, xf == bxa, xf == bxb, at_ya, at_yb, b.depth + (size_t)b.nx * by1 + bx1, b.nx);
-        }
-        dhdx = gh.x; dhdy = gh.y;
-    } else {
-        float gx32, gy32;
-        bathy_analytic(BK, b, xf, yf, h32, gx32, gy32);
-        dhdx = (double)gx32; dhdy = (double)gy32;
-    }
-    CurrentVal cv;
-    if (CK == MR_CURRENT_GRID) {
-        float c01 = c.c01, c10 = c.c10;
-        if (UNI) {
-            cxa = __fmaf_rn((float)cx1, c.dxf, c.xf0); cxb = __fadd_rn(cxa, c.dxf);
-            cya = __fmaf_rn((float)cy1, c.dyf, c.yf0); cyb = __fadd_rn(cya, c.dyf);
-        } else {
-            const float dx = __fsub_rn(cxb, cxa), dy = __fsub_rn(cyb, cya);
-            const float det = __fsub_rn(0.0f, __fmul_rn(dx, dy));
-            ok = ok && det != 0.0f;
-            c01 = -__fdiv_rn(dx, det); c10 = -__fdiv_rn(dy, det);
-        }
-        const float X = __fmul_rn(c01, __fsub_rn(yf, cya)), Y = __fmul_rn(c10, __fsub_rn(xf, cxa));
-        float u32 = bilinear_xy(X, Y, U);
-        float v32 = bilinear_xy(X, Y, V);
-        if (xf == cxa || xf == cxb) {
-            const bool at_ya = yf == cya, at_yb = yf == cyb;
-            if (at_ya || at_yb) {
-                const size_t node = (size_t)c.nx * cy1 + cx1;
-                u32 = corner_pick(u32, xf == cxa, xf == cxb, at_ya, at_yb, c.u + node, c.nx);
-                v32 = corner_pick(v32, xf == cxa, xf == cxb, at_ya, at_yb, c.v + node, c.nx);
+
+    // ---- phase 2: all record loads -----------------------------------------------------------------
+    __device__ __forceinline__ void phase2(const BathyDev &b, const CurrentDev &c)
+    {
+        if (BK == MR_BATHY_GRID) {
+            ldg_f4_d2(brec, Z, gh);
+            if (!UNI) {
+                bxa = __ldg(b.x + bx1); bxb = __ldg(b.x + bx1 + 1);
+                bya = __ldg(b.y + by1); byb = __ldg(b.y + by1 + 1);
             }
         }
-        cv.u = (double)u32; cv.v = (double)v32;
-        cv.dudx = gu.x; cv.dudy = gu.y; cv.dvdx = gv.x; cv.dvdy = gv.y;
-    } else {
-        cv.u = c.u0; cv.v = c.v0; cv.dudx = cv.dudy = cv.dvdx = cv.dvdy = 0.0;   // constant_current.rs:69-77
+        if (CK == MR_CURRENT_GRID) {
+            ldg_f4_f4(c.cell + 4u * ccell, U, V);
+            ldg_d2_d2((const double2 *)(c.cell + 4u * ccell + 2), gu, gv);
+            if (!UNI) {
+                cxa = __ldg(c.xf + cx1); cxb = __ldg(c.xf + cx1 + 1);
+                cya = __ldg(c.yf + cy1); cyb = __ldg(c.yf + cy1 + 1);
+            }
+        }
     }
-    // h <= 0 -> cg = NaN and the bathymetric term is NaN too (inf*0 or sqrt of a negative);
-    // k == 0 -> Err (wave_ray_path.rs:178-183): all four NaN, like a failed lookup
-    ok = ok && h32 > 0.0f && k2 > 0.0;
-    const double h = ok ? (double)h32 : qnan();
-    rhs_f64_fast(kx, ky, k, cs, sn, h, dhdx, dhdy, cv, out);
+
+    // ---- phase 3: wavenumber-only f64 work, under the loads --------------------------------------
+    __device__ __forceinline__ void phase3(double kx, double ky)
+    {
+        k2 = fma(kx, kx, ky * ky);
+        double rk;
+        sqrt_rsqrt(k2, k, rk);
+        cs = kx * rk; sn = ky * rk;
+    }
+
+    // ---- phase 4: f32 bilinears, then the f64 stage --------------------------------------------------
+    __device__ __forceinline__ void phase4(const BathyDev &b, const CurrentDev &c, double kx, double ky, double out[4])
+    {
+        // Scheduling fence.  ptxas places the first consumer of the bathymetry record ahead of the
+        // current record's loads (whose f64 address chain is longer), so a warp waited for one L2
+        // round trip, issued the other loads, and waited again (profiles/r1/g_*).  OR-ing in
+        // (bits of the current record) & 0 — a zero the compiler cannot see — changes no value but
+        // makes the first bathymetry consumer depend on both loads, so both are in flight first.
+        if (BK == MR_BATHY_GRID && CK == MR_CURRENT_GRID)
+            Z.x = __int_as_float(__float_as_int(Z.x) | (__float_as_int(U.x) & b.zero));
+        float h32;
+        double dhdx, dhdy;
+        if (BK == MR_BATHY_GRID) {
+            float c01 = b.c01, c10 = b.c10;
+            if (UNI) {
+                bxa = __fmaf_rn((float)bx1, b.dxf, b.xf0); bxb = __fadd_rn(bxa, b.dxf);
+                bya = __fmaf_rn((float)by1, b.dyf, b.yf0); byb = __fadd_rn(bya, b.dyf);
+            } else {
+                const float dx = __fsub_rn(bxb, bxa), dy = __fsub_rn(byb, bya);
+                const float det = __fsub_rn(0.0f, __fmul_rn(dx, dy));              // interpolator.rs:64
+                ok = ok && det != 0.0f;                                            // :65-67
+                c01 = -__fdiv_rn(dx, det); c10 = -__fdiv_rn(dy, det);              // :70-71
+            }
+            const float X = __fmul_rn(c01, __fsub_rn(yf, bya)), Y = __fmul_rn(c10, __fsub_rn(xf, bxa));
+            h32 = bilinear_xy(X, Y, Z);
+            if (xf == bxa || xf == bxb) {
+                const bool at_ya = yf == bya, at_yb = yf == byb;
+                if (at_ya || at_yb)
+                    h32 = corner_pick(h32, xf == bxa, xf == bxb, at_ya, at_yb, b.depth + (size_t)b.nx * by1 + bx1, b.nx);
+            }
+            dhdx = gh.x; dhdy = gh.y;
+        } else {
+            float gx32, gy32;
+            bathy_analytic(BK, b, xf, yf, h32, gx32, gy32);
+            dhdx = (double)gx32; dhdy = (double)gy32;
+        }
+        CurrentVal cv;
+        if (CK == MR_CURRENT_GRID) {
+            float c01 = c.c01, c10 = c.c10;
+            if (UNI) {
+                cxa = __fmaf_rn((float)cx1, c.dxf, c.xf0); cxb = __fadd_rn(cxa, c.dxf);
+                cya = __fmaf_rn((float)cy1, c.dyf, c.yf0); cyb = __fadd_rn(cya, c.dyf);
+            } else {
+                const float dx = __fsub_rn(cxb, cxa), dy = __fsub_rn(cyb, cya);
+                const float det = __fsub_rn(0.0f, __fmul_rn(dx, dy));
+                ok = ok && det != 0.0f;
+                c01 = -__fdiv_rn(dx, det); c10 = -__fdiv_rn(dy, det);
+            }
+            const float X = __fmul_rn(c01, __fsub_rn(yf, cya)), Y = __fmul_rn(c10, __fsub_rn(xf, cxa));
+            float u32 = bilinear_xy(X, Y, U);
+            float v32 = bilinear_xy(X, Y, V);
+            if (xf == cxa || xf == cxb) {
+                const bool at_ya = yf == cya, at_yb = yf == cyb;
+                if (at_ya || at_yb) {
+                    const size_t node = (size_t)c.nx * cy1 + cx1;
+                    u32 = corner_pick(u32, xf == cxa, xf == cxb, at_ya, at_yb, c.u + node, c.nx);
+                    v32 = corner_pick(v32, xf == cxa, xf == cxb, at_ya, at_yb, c.v + node, c.nx);
+                }
+            }
+            cv.u = (double)u32; cv.v = (double)v32;
+            cv.dudx = gu.x; cv.dudy = gu.y; cv.dvdx = gv.x; cv.dvdy = gv.y;
+        } else {
+            cv.u = c.u0; cv.v = c.v0; cv.dudx = cv.dudy = cv.dvdx = cv.dvdy = 0.0;   // constant_current.rs:69-77
+        }
+        // h <= 0 -> cg = NaN and the bathymetric term is NaN too (inf*0 or sqrt of a negative);
+        // k == 0 -> Err (wave_ray_path.rs:178-183): all four NaN, like a failed lookup
+        ok = ok && h32 > 0.0f && k2 > 0.0;
+        const double h = ok ? (double)h32 : qnan();
+        rhs_f64_fast(kx, ky, k, cs, sn, h, dhdx, dhdy, cv, out);
+    }
+};
+
+// The RHS of NR rays carried by one thread, phase by phase.
+template <int BK, int CK, bool UNI, int NR>
+__device__ __forceinline__ void rhs_fast_n(const BathyDev &b, const CurrentDev &c,
+                                           const double (&s)[NR][4], double (&out)[NR][4])
+{
+    FastRay<BK, CK, UNI> ray[NR];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) ray[r].phase1(b, c, s[r][0], s[r][1]);
+#pragma unroll
+    for (int r = 0; r < NR; ++r) ray[r].phase2(b, c);
+#pragma unroll
+    for (int r = 0; r < NR; ++r) ray[r].phase3(s[r][2], s[r][3]);
+#pragma unroll
+    for (int r = 0; r < NR; ++r) ray[r].phase4(b, c, s[r][2], s[r][3], out[r]);
 }
 
 // =============================================================================
 // System::system (wave_ray_path.rs:220-234): Err -> four NaN
 // =============================================================================
-template <int BK, int CK, int MATH, bool UNI>
+template <int BK, int CK, int MATH, bool UNI, int NR>
 __device__ __forceinline__ void rhs(const BathyDev &b, const CurrentDev &c,
-                                    double x, double y, double kx, double ky, double out[4])
+                                    const double (&s)[NR][4], double (&out)[NR][4])
 {
-    const float xf = (float)x, yf = (float)y;                                  // :122
-    float h32, gx32, gy32;
-    CurrentVal cv;
     if (MATH == MR_MATH_STRICT) {
-        bool ok = (BK == MR_BATHY_GRID) ? bathy_grid_strict(b, xf, yf, h32, gx32, gy32)
-                                        : bathy_analytic(BK, b, xf, yf, h32, gx32, gy32);   // :120-122
-        if (ok) {
-            if (CK == MR_CURRENT_GRID) ok = current_grid_strict(c, x, y, cv);              // :129
-            else { cv.u = c.u0; cv.v = c.v0; cv.dudx = cv.dudy = cv.dvdx = cv.dvdy = 0.0; }
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            const double x = s[r][0], y = s[r][1], kx = s[r][2], ky = s[r][3];
+            const float xf = (float)x, yf = (float)y;                                  // :122
+            float h32, gx32, gy32;
+            CurrentVal cv;
+            bool ok = (BK == MR_BATHY_GRID) ? bathy_grid_strict(b, xf, yf, h32, gx32, gy32)
+                                            : bathy_analytic(BK, b, xf, yf, h32, gx32, gy32);   // :120-122
+            if (ok) {
+                if (CK == MR_CURRENT_GRID) ok = current_grid_strict(c, x, y, cv);              // :129
+                else { cv.u = c.u0; cv.v = c.v0; cv.dudx = cv.dudy = cv.dvdx = cv.dvdy = 0.0; }
+            }
+            if (!ok) out[r][0] = out[r][1] = out[r][2] = out[r][3] = qnan();
+            else rhs_f64_strict(kx, ky, (double)h32, (double)gx32, (double)gy32, cv, out[r]);
         }
-        if (!ok) {
-            out[0] = out[1] = out[2] = out[3] = qnan();
-            return;
-        }
-        rhs_f64_strict(kx, ky, (double)h32, (double)gx32, (double)gy32, cv, out);
     } else {
-        rhs_fast<BK, CK, UNI>(b, c, x, y, kx, ky, xf, yf, out);
+        rhs_fast_n<BK, CK, UNI, NR>(b, c, s, out);
     }
 }
 

@@ -239,7 +239,7 @@ def _opts(stride: int, math: int, chunk_rays: int) -> _abi.TraceOpts:
 
 def trace_many(fields: Fields, x0, y0, kx0, ky0, t0: float, t_end: float, dt: float, *,
                stride: int = 1, math: int = _abi.MR_MATH_FAST, chunk_rays: int = 0,
-               trajectories: bool = True, final_state: bool = False, pinned: bool = False) -> TraceResult:
+               trajectories: bool = True, final_state: bool = False, pinned: Optional[bool] = False) -> TraceResult:
     """``mr_trace_many`` on numpy arrays."""
     lib = load()
     x0 = np.ascontiguousarray(x0, dtype=np.float64).ravel()
@@ -250,7 +250,18 @@ def trace_many(fields: Fields, x0, y0, kx0, ky0, t0: float, t_end: float, dt: fl
     nsteps = num_steps(t0, t_end, dt)
     stride = max(int(stride), 1)
     rows_cap = nsteps // stride + 1
-    alloc = pinned_empty if pinned else (lambda shape, dtype=np.float64: np.empty(shape, dtype=dtype))
+    def alloc(shape, dtype=np.float64):
+        # page-locked planes let the device-to-host gather run at PCIe rate and overlap the kernels;
+        # pinned=None picks them for outputs large enough to matter and falls back if the driver refuses
+        nbytes = int(np.prod(shape, dtype=np.int64)) * np.dtype(dtype).itemsize
+        if pinned or (pinned is None and nbytes >= (32 << 20)):
+            try:
+                return pinned_empty(shape, dtype)
+            except (MantarayError, MemoryError):
+                if pinned:
+                    raise
+        return np.empty(shape, dtype=dtype)
+
     t = np.empty(rows_cap, dtype=np.float64)
     if trajectories:
         x, y, kx, ky = (alloc((rows_cap, n)) for _ in range(4))

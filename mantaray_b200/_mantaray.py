@@ -78,5 +78,5 @@ def ray_tracing(x0, y0, kx0, ky0, duration: float, step_size: float,
     if n < 4096:                         # not worth more than one device
         dev = dev[:1]
     with _capi.Fields.open_netcdf3(str(bathymetry_filename), str(current_filename), devices=dev) as f:
-        res = _capi.trace_many(f, x0, y0, kx0, ky0, 0.0, duration, step_size, math=MR_MATH_FAST)
+        res = _capi.trace_many(f, x0, y0, kx0, ky0, 0.0, duration, step_size, math=MR_MATH_FAST, pinned=None)
     return RayBundle(res)

@@ -194,8 +194,10 @@ __global__ void build_current_cells(const double *u, const double *v, int nx, in
         const double *pu = u + (size_t)nx * y1 + x1, *pv = v + (size_t)nx * y1 + x1;
         const double usw = pu[0], use_ = pu[1], unw = pu[nx], une = pu[nx + 1];
         const double vsw = pv[0], vse = pv[1], vnw = pv[nx], vne = pv[nx + 1];
-        cell[4 * i] = bilinear_coeffs((float)usw, (float)unw, (float)une, (float)use_);
-        cell[4 * i + 1] = bilinear_coeffs((float)vsw, (float)vnw, (float)vne, (float)vse);
+        const float4 cu = bilinear_coeffs((float)usw, (float)unw, (float)une, (float)use_);
+        const float4 cv = bilinear_coeffs((float)vsw, (float)vnw, (float)vne, (float)vse);
+        cell[4 * i] = make_float4(cu.x, cv.x, cu.y, cv.y);          // interleaved for the packed (u, v) bilinear
+        cell[4 * i + 1] = make_float4(cu.z, cv.z, cu.w, cv.w);
         double2 *g = reinterpret_cast<double2 *>(cell + 4 * i + 2);
         g[0] = make_double2(__ddiv_rn(__dsub_rn(use_, usw), x_space), __ddiv_rn(__dsub_rn(unw, usw), y_space));
         g[1] = make_double2(__ddiv_rn(__dsub_rn(vse, vsw), x_space), __ddiv_rn(__dsub_rn(vnw, vsw), y_space));
@@ -275,8 +277,15 @@ static int upload_fields(DeviceFields &d, const mr_bathymetry_desc *b, const mr_
         B.cell = cell;
         B.nxm1f = (float)(b->nx - 1); B.nym1f = (float)(b->ny - 1);
         B.zero = 0;
+        auto pack2 = [](float lo, float hi) {
+            uint32_t a, b2;
+            std::memcpy(&a, &lo, 4); std::memcpy(&b2, &hi, 4);
+            return (unsigned long long)a | ((unsigned long long)b2 << 32);
+        };
         B.uniform = affine_f32(b->x, b->nx, &B.dxf) && affine_f32(b->y, b->ny, &B.dyf) &&
                     basis_coeffs(B.dxf, B.dyf, &B.c01, &B.c10) && recip_ok(B.sx, &B.rsx) && recip_ok(B.sy, &B.rsy);
+        B.p0 = pack2(B.xf0, B.yf0); B.rs2 = pack2(B.rsx, B.rsy); B.ns2 = pack2(-B.sx, -B.sy);
+        B.d2 = pack2(B.dxf, B.dyf); B.c2 = pack2(B.c10, B.c01);
     } else if (b->kind == MR_BATHY_ARRAY) {
         int rc;
         if ((rc = upload(d, b->array, (size_t)b->nx * b->ny, &B.array))) return rc;
@@ -310,6 +319,12 @@ static int upload_fields(DeviceFields &d, const mr_bathymetry_desc *b, const mr_
         C.xf0 = xf[0]; C.yf0 = yf[0];
         C.uniform = affine_f32(xf.data(), c->nx, &C.dxf) && affine_f32(yf.data(), c->ny, &C.dyf) &&
                     basis_coeffs(C.dxf, C.dyf, &C.c01, &C.c10);
+        auto pack2c = [](float lo, float hi) {
+            uint32_t a, b2;
+            std::memcpy(&a, &lo, 4); std::memcpy(&b2, &hi, 4);
+            return (unsigned long long)a | ((unsigned long long)b2 << 32);
+        };
+        C.p0 = pack2c(C.xf0, C.yf0); C.d2 = pack2c(C.dxf, C.dyf); C.c2 = pack2c(C.c10, C.c01);
     }
     MR_CUDA(cudaDeviceSynchronize());
     return MR_OK;

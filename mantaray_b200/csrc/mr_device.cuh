@@ -29,6 +29,8 @@
 
 namespace mr {
 
+typedef unsigned long long f32x2;    // two f32 in one 64-bit register (lo, hi), see the packed helpers below
+
 // ---- device-resident field descriptors (passed by value as kernel params) ----
 
 struct BathyDev {
@@ -53,6 +55,8 @@ struct BathyDev {
     // corner coordinates and the change-of-basis coefficients become launch constants
     int32_t uniform;
     float dxf, dyf, c01, c10;
+    // the same constants as (x, y) pairs for the packed f32 path
+    f32x2 p0, rs2, ns2, d2, c2;   // {x0,y0} {1/sx,1/sy} {-sx,-sy} {dx,dy} {c10,c01}
 };
 
 struct CurrentDev {
@@ -65,13 +69,15 @@ struct CurrentDev {
     double sx, sy;             // |x[1]-x[0]|, |y[1]-y[0]|          (cartesian_current.rs:244)
     double inv_sx, inv_sy;     // RN(1/sx), RN(1/sy)
     double x_space, y_space;   // x[1]-x[0] (signed)                (cartesian_current.rs:515-516)
-    // fast path: one 64-byte record per cell: float4 bilinear_coeffs of the u corners, float4 of the v
-    // corners (as f32), double2 {dudx,dudy}, double2 {dvdx,dvdy} (the f64 finite differences, divided)
+    // fast path: one 64-byte record per cell: the bilinear_coeffs of the u and of the v corners (as f32)
+    // interleaved {u_sw,v_sw,u_a10,v_a10}, {u_a01,v_a01,u_a11,v_a11}, then double2 {dudx,dudy}, double2
+    // {dvdx,dvdy} (the f64 finite differences, divided)
     const float4 *cell;
     const float *xf, *yf;      // coordinates cast to f32 (cartesian_current.rs:375-376)
     double nxm1d, nym1d;       // (nx-1), (ny-1) as f64: the bound of cartesian_current.rs:248
     int32_t uniform;
     float xf0, yf0, dxf, dyf, c01, c10;
+    f32x2 p0, d2, c2;          // {x0,y0} {dx,dy} {c10,c01} as f32 pairs
 };
 
 static constexpr double kG = 9.8;            // src/wave_ray_path.rs:23
@@ -133,6 +139,23 @@ __device__ __forceinline__ bool bilinear_cell_strict(float xa, float xb, float y
     out = r;
     return true;
 }
+
+// ---- packed f32 pairs (sm_100 FADD2 / FMUL2 / FFMA2) ------------------------------------------
+// Two IEEE round-to-nearest f32 operations per instruction: each half is exactly the scalar _rn
+// operation, so the reference's f32 arithmetic can be done two components at a time — (x, y)
+// for indices and coordinates, (u, v) for the two current bilinears — at half the issue slots.
+__device__ __forceinline__ f32x2 pk(float lo, float hi)
+{
+    f32x2 r;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ float lo_of(f32x2 v) { return __uint_as_float((unsigned)v); }
+__device__ __forceinline__ float hi_of(f32x2 v) { return __uint_as_float((unsigned)(v >> 32)); }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { f32x2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
 
 // fast form.  The cell's fractional coordinates (X, Y) are resolved once per lookup and shared by
 // every variable interpolated on that cell; the corner combinations a10 = z_nw - z_sw,
@@ -500,8 +523,12 @@ struct FastRay {
         if (BK == MR_BATHY_GRID) {
             float ix, iy;                                                          // cartesian_netcdf3.rs:289
             if (UNI) {
-                ix = fdiv_const(__fsub_rn(xf, b.xf0), b.sx, b.rsx);
-                iy = fdiv_const(__fsub_rn(yf, b.yf0), b.sy, b.rsy);
+                // fdiv_const for x and y at once: t = p - p0; q = t*r; twice q += (t - q*s)*r
+                const f32x2 t = sub2(pk(xf, yf), b.p0);
+                f32x2 q = mul2(t, b.rs2);
+                q = fma2(fma2(q, b.ns2, t), b.rs2, q);
+                q = fma2(fma2(q, b.ns2, t), b.rs2, q);
+                ix = lo_of(q); iy = hi_of(q);
             } else {
                 ix = __fdiv_rn(__fsub_rn(xf, b.xf0), b.sx);
                 iy = __fdiv_rn(__fsub_rn(yf, b.yf0), b.sy);
@@ -564,20 +591,25 @@ struct FastRay {
         // makes the first bathymetry consumer depend on both loads, so both are in flight first.
         if (BK == MR_BATHY_GRID && CK == MR_CURRENT_GRID)
             Z.x = __int_as_float(__float_as_int(Z.x) | (__float_as_int(U.x) & b.zero));
+        const f32x2 p = pk(xf, yf);
         float h32;
         double dhdx, dhdy;
         if (BK == MR_BATHY_GRID) {
-            float c01 = b.c01, c10 = b.c10;
+            float X, Y;
             if (UNI) {
-                bxa = __fmaf_rn((float)bx1, b.dxf, b.xf0); bxb = __fadd_rn(bxa, b.dxf);
-                bya = __fmaf_rn((float)by1, b.dyf, b.yf0); byb = __fadd_rn(bya, b.dyf);
+                // corner coordinates (xa,ya) = i*d + p0 and (xb,yb) = (xa,ya) + d, then
+                // (Y, X) = (c10, c01) * ((x,y) - (xa,ya)), two components per instruction
+                const f32x2 pa = fma2(pk((float)bx1, (float)by1), b.d2, b.p0), pb = add2(pa, b.d2);
+                const f32x2 yx = mul2(b.c2, sub2(p, pa));
+                bxa = lo_of(pa); bya = hi_of(pa); bxb = lo_of(pb); byb = hi_of(pb);
+                Y = lo_of(yx); X = hi_of(yx);
             } else {
                 const float dx = __fsub_rn(bxb, bxa), dy = __fsub_rn(byb, bya);
                 const float det = __fsub_rn(0.0f, __fmul_rn(dx, dy));              // interpolator.rs:64
                 ok = ok && det != 0.0f;                                            // :65-67
-                c01 = -__fdiv_rn(dx, det); c10 = -__fdiv_rn(dy, det);              // :70-71
+                const float c01 = -__fdiv_rn(dx, det), c10 = -__fdiv_rn(dy, det);  // :70-71
+                X = __fmul_rn(c01, __fsub_rn(yf, bya)); Y = __fmul_rn(c10, __fsub_rn(xf, bxa));
             }
-            const float X = __fmul_rn(c01, __fsub_rn(yf, bya)), Y = __fmul_rn(c10, __fsub_rn(xf, bxa));
             h32 = bilinear_xy(X, Y, Z);
             if (xf == bxa || xf == bxb) {
                 const bool at_ya = yf == bya, at_yb = yf == byb;
@@ -592,19 +624,30 @@ struct FastRay {
         }
         CurrentVal cv;
         if (CK == MR_CURRENT_GRID) {
-            float c01 = c.c01, c10 = c.c10;
+            float X, Y;
             if (UNI) {
-                cxa = __fmaf_rn((float)cx1, c.dxf, c.xf0); cxb = __fadd_rn(cxa, c.dxf);
-                cya = __fmaf_rn((float)cy1, c.dyf, c.yf0); cyb = __fadd_rn(cya, c.dyf);
+                const f32x2 pa = fma2(pk((float)cx1, (float)cy1), c.d2, c.p0), pb = add2(pa, c.d2);
+                const f32x2 yx = mul2(c.c2, sub2(p, pa));
+                cxa = lo_of(pa); cya = hi_of(pa); cxb = lo_of(pb); cyb = hi_of(pb);
+                Y = lo_of(yx); X = hi_of(yx);
             } else {
                 const float dx = __fsub_rn(cxb, cxa), dy = __fsub_rn(cyb, cya);
                 const float det = __fsub_rn(0.0f, __fmul_rn(dx, dy));
                 ok = ok && det != 0.0f;
-                c01 = -__fdiv_rn(dx, det); c10 = -__fdiv_rn(dy, det);
+                const float c01 = -__fdiv_rn(dx, det), c10 = -__fdiv_rn(dy, det);
+                X = __fmul_rn(c01, __fsub_rn(yf, cya)); Y = __fmul_rn(c10, __fsub_rn(xf, cxa));
             }
-            const float X = __fmul_rn(c01, __fsub_rn(yf, cya)), Y = __fmul_rn(c10, __fsub_rn(xf, cxa));
-            float u32 = bilinear_xy(X, Y, U);
-            float v32 = bilinear_xy(X, Y, V);
+            // u and v together (interpolator.rs:83 on both): the record interleaves their coefficients,
+            // U = {u_sw, v_sw, u_a10, v_a10}, V = {u_a01, v_a01, u_a11, v_a11}
+            // The products go two at a time; the sums stay scalar add.rn: ptxas (12.9) contracts a
+            // mul.rn.f32x2 feeding an add.rn.f32x2 into one FFMA2 — even with -fmad=false — which would
+            // drop the rounding of the product that the reference performs.
+            const f32x2 XX = pk(X, X), YY = pk(Y, Y);
+            const f32x2 m10 = mul2(pk(U.z, U.w), XX);
+            const f32x2 m01 = mul2(pk(V.x, V.y), YY);
+            const f32x2 m11 = mul2(mul2(pk(V.z, V.w), XX), YY);
+            float u32 = __fadd_rn(__fadd_rn(__fadd_rn(U.x, lo_of(m10)), lo_of(m01)), lo_of(m11));
+            float v32 = __fadd_rn(__fadd_rn(__fadd_rn(U.y, hi_of(m10)), hi_of(m01)), hi_of(m11));
             if (xf == cxa || xf == cxb) {
                 const bool at_ya = yf == cya, at_yb = yf == cyb;
                 if (at_ya || at_yb) {

@@ -89,3 +89,31 @@ def test_c5_nazare_8m_ray_shard_decimated(oracle, gpu):
     np.testing.assert_array_equal(res.len[sel], ref.len)
     _final_state_close(res.final_state[:, sel], ref.final_state)
     assert ref.rows.min() < 4097 == ref.rows.max()      # built-in load imbalance: some rays stop early
+
+
+def test_c1_canonical_through_the_python_api(oracle, gpu, tmp_path):
+    """configs[0], the reference's own CPU-runnable case, through `mantaray.ray_tracing` and NetCDF files:
+    constant depth 4000 m, zero current on 200x100 @ 1 km, 1 000 rays, dt 2.5 s, 10 000 steps."""
+    import mantaray
+    from mantaray_b200.io_utility import write_netcdf3
+
+    wl = W.c1_canonical()
+    b, c = wl.bathymetry, wl.current
+    write_netcdf3(tmp_path / "bathy.nc", [("y", b.y.size), ("x", b.x.size)],
+                  {"x": (["x"], b.x), "y": (["y"], b.y), "depth": (["y", "x"], b.depth.reshape(b.y.size, b.x.size))})
+    write_netcdf3(tmp_path / "cur.nc", [("y", c.y.size), ("x", c.x.size)],
+                  {"x": (["x"], c.x), "y": (["y"], c.y), "u": (["y", "x"], c.u.reshape(c.y.size, c.x.size)),
+                   "v": (["y", "x"], c.v.reshape(c.y.size, c.x.size))})
+    x0, y0, kx0, ky0 = wl.all_rays()
+    ds = mantaray.ray_tracing(x0, y0, kx0, ky0, wl.duration, wl.dt, str(tmp_path / "bathy.nc"), str(tmp_path / "cur.nc"))
+    assert ds.sizes["time_step"] == 10_001 and ds.sizes["ray"] == 1000
+    kx, ky, x = np.asarray(ds.kx), np.asarray(ds.ky), np.asarray(ds.x)
+    assert (kx == kx0[0]).all() and (ky == 0.0).all()               # constant fields: k is conserved bit for bit
+    assert not np.isnan(x).any() and (np.diff(x, axis=0) > 0).all()  # nobody leaves the 199 km domain
+    np.testing.assert_array_equal(np.asarray(ds.time)[:, 0], np.asarray(ds.time)[:, -1])
+    sel = np.arange(0, 1000, 100)
+    ref = oracle.trace_many(b, c, x0[sel], y0[sel], kx0[sel], ky0[sel], 0.0, wl.duration, wl.dt)
+    scale = np.abs(ref.x).max()
+    assert np.abs(x[:, sel] - ref.x).max() <= REL_TOL * scale
+    assert np.abs(np.asarray(ds.y)[:, sel] - ref.y).max() <= REL_TOL * scale
+    np.testing.assert_array_equal(np.asarray(ds.time)[:, 0], ref.t)

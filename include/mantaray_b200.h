@@ -217,6 +217,46 @@ int  mr_trace_device(mr_fields *f, int device, void *stream, int64_t n,
                      double *d_x, double *d_y, double *d_kx, double *d_ky, int64_t ld,
                      int32_t *d_rows, int32_t *d_len, double *d_final, int32_t *launches);
 
+/* ---- environment along rays ------------------------------------------------ */
+
+/*
+ * The reference sketches a per-ray record Ray{time, state, depth: Vec<f32>,
+ * current: Vec<Current<T>>} (src/datatype.rs:165-194) that nothing fills yet.
+ * These entry points produce its depth and current columns: the fields
+ * evaluated at points, by the reference's own accessors
+ *   depth = BathymetryData::depth(&Point<f32>)   src/bathymetry/mod.rs:38
+ *           (the point is (x as f32, y as f32), src/wave_ray_path.rs:122)
+ *   u, v  = CurrentData::current(&Point<f64>)    src/current/mod.rs:24
+ * operation by operation; where the accessor returns Err (outside the grid)
+ * the value is NaN.  ConstantCurrent ignores the point, NaN or not
+ * (src/current/constant_current.rs:51-53), and so does this.
+ */
+typedef struct mr_env_planes {
+    float  *depth;             /* [rows_cap][n] or NULL */
+    double *u, *v;             /* [rows_cap][n] or NULL */
+} mr_env_planes;
+
+/* mr_trace_many plus the environment at every stored row (same layout as x:
+ * depth[j*n + i]).  Needs the x, y, kx, ky planes.  env == NULL, or all three
+ * planes NULL, is mr_trace_many. */
+int  mr_trace_many_env(mr_fields *f, int64_t n,
+                       const double *x0, const double *y0, const double *kx0, const double *ky0,
+                       double t0, double t_end, double dt, const mr_trace_opts *opts,
+                       double *t, double *x, double *y, double *kx, double *ky,
+                       int32_t *rows, int32_t *len, double *final_state,
+                       const mr_env_planes *env);
+
+/* The fields at `count` arbitrary points (HOST arrays; outputs may be NULL).
+ * Runs on the first device of the handle. */
+int  mr_sample_fields(mr_fields *f, int64_t count, const double *x, const double *y,
+                      float *depth, double *u, double *v);
+
+/* Device-resident: points laid out [rows][ld] (n <= ld used per row), e.g. the
+ * d_x, d_y planes of mr_trace_device.  Asynchronous on `stream`. */
+int  mr_sample_device(mr_fields *f, int device, void *stream, int64_t rows, int64_t n, int64_t ld,
+                      const double *d_x, const double *d_y,
+                      float *d_depth, double *d_u, double *d_v, int32_t *launches);
+
 /* ---- NetCDF-3 ingest -------------------------------------------------------- */
 
 /*

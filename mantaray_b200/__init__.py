@@ -9,14 +9,14 @@ library, calling into it does (and fails loudly when it is missing).
 """
 
 from ._abi import MR_MATH_FAST, MR_MATH_STRICT
-from ._capi import Fields, ManyRays, MantarayError, RayState, SingleRay, TraceResult, trace_many
+from ._capi import Fields, ManyRays, MantarayError, RayState, SingleRay, TraceResult, sample_fields, trace_many
 from .core import ray_tracing, single_ray
 from .fields import (ArrayDepth, CartesianCurrent, CartesianNetcdf3, ConstantCurrent, ConstantDepth,
                      ConstantSlope)
 
 __all__ = [
     "single_ray", "ray_tracing",
-    "ManyRays", "SingleRay", "RayState", "Fields", "TraceResult", "trace_many", "MantarayError",
+    "ManyRays", "SingleRay", "RayState", "Fields", "TraceResult", "trace_many", "sample_fields", "MantarayError",
     "ConstantDepth", "ConstantSlope", "CartesianNetcdf3", "ArrayDepth", "ConstantCurrent", "CartesianCurrent",
     "MR_MATH_FAST", "MR_MATH_STRICT",
 ]

@@ -81,6 +81,12 @@ class TraceOpts(C.Structure):
     ]
 
 
+class EnvPlanes(C.Structure):
+    """``mr_env_planes``"""
+
+    _fields_ = [("depth", C.c_void_p), ("u", C.c_void_p), ("v", C.c_void_p)]
+
+
 #: every symbol the header declares: name -> (restype, argtypes)
 SIGNATURES = {
     "mr_abi_version": (C.c_int, []),
@@ -101,6 +107,22 @@ SIGNATURES = {
          C.c_double, C.c_double, C.c_double, C.POINTER(TraceOpts),
          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
          C.c_void_p, C.c_void_p, C.c_void_p],
+    ),
+    "mr_trace_many_env": (
+        C.c_int,
+        [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+         C.c_double, C.c_double, C.c_double, C.POINTER(TraceOpts),
+         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+         C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(EnvPlanes)],
+    ),
+    "mr_sample_fields": (
+        C.c_int,
+        [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
+    ),
+    "mr_sample_device": (
+        C.c_int,
+        [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
+         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, c_int32_p],
     ),
     "mr_single_ray": (
         C.c_int,

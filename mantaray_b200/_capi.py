@@ -224,6 +224,10 @@ class TraceResult:
     len: np.ndarray
     final_state: Optional[np.ndarray]
     stride: int = 1
+    #: the environment at every stored row (``env=True``): depth f32, current f64, ``(rows_cap, n)``
+    depth: Optional[np.ndarray] = None
+    u: Optional[np.ndarray] = None
+    v: Optional[np.ndarray] = None
 
 
 def num_steps(t0: float, t_end: float, dt: float) -> int:
@@ -239,8 +243,9 @@ def _opts(stride: int, math: int, chunk_rays: int) -> _abi.TraceOpts:
 
 def trace_many(fields: Fields, x0, y0, kx0, ky0, t0: float, t_end: float, dt: float, *,
                stride: int = 1, math: int = _abi.MR_MATH_FAST, chunk_rays: int = 0,
-               trajectories: bool = True, final_state: bool = False, pinned: Optional[bool] = False) -> TraceResult:
-    """``mr_trace_many`` on numpy arrays."""
+               trajectories: bool = True, final_state: bool = False, pinned: Optional[bool] = False,
+               env: bool = False) -> TraceResult:
+    """``mr_trace_many`` on numpy arrays; ``env=True`` adds depth, u, v at every stored row (``mr_trace_many_env``)."""
     lib = load()
     x0 = np.ascontiguousarray(x0, dtype=np.float64).ravel()
     y0 = np.ascontiguousarray(y0, dtype=np.float64).ravel()
@@ -272,10 +277,36 @@ def trace_many(fields: Fields, x0, y0, kx0, ky0, t0: float, t_end: float, dt: fl
     fin = np.empty((4, n), dtype=np.float64) if final_state else None
     o = _opts(stride, math, chunk_rays)
     ptr = lambda a: a.ctypes.data if a is not None else None
+    if env:
+        if not trajectories:
+            raise ValueError("env=True needs trajectories=True")
+        depth, u, v = alloc((rows_cap, n), np.float32), alloc((rows_cap, n)), alloc((rows_cap, n))
+        planes = _abi.EnvPlanes(ptr(depth), ptr(u), ptr(v))
+        _check(lib.mr_trace_many_env(fields.handle, n, ptr(x0), ptr(y0), ptr(kx0), ptr(ky0),
+                                     float(t0), float(t_end), float(dt), C.byref(o),
+                                     ptr(t), ptr(x), ptr(y), ptr(kx), ptr(ky), ptr(rows), ptr(length), ptr(fin),
+                                     C.byref(planes)))
+        return TraceResult(t, x, y, kx, ky, rows, length, fin, stride, depth, u, v)
     _check(lib.mr_trace_many(fields.handle, n, ptr(x0), ptr(y0), ptr(kx0), ptr(ky0),
                              float(t0), float(t_end), float(dt), C.byref(o),
                              ptr(t), ptr(x), ptr(y), ptr(kx), ptr(ky), ptr(rows), ptr(length), ptr(fin)))
     return TraceResult(t, x, y, kx, ky, rows, length, fin, stride)
+
+
+def sample_fields(fields: Fields, x, y):
+    """``mr_sample_fields``: ``(depth f32, u, v)`` of the fields at points, by the reference's ``depth()``
+    (src/bathymetry/mod.rs:38) and ``current()`` (src/current/mod.rs:24); NaN where they return Err."""
+    lib = load()
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    if x.shape != y.shape:
+        raise ValueError("x and y must have the same shape")
+    depth = np.empty(x.shape, dtype=np.float32)
+    u = np.empty(x.shape, dtype=np.float64)
+    v = np.empty(x.shape, dtype=np.float64)
+    _check(lib.mr_sample_fields(fields.handle, x.size, x.ctypes.data, y.ctypes.data,
+                                depth.ctypes.data, u.ctypes.data, v.ctypes.data))
+    return depth, u, v
 
 
 def single_ray(fields: Fields, x0: float, y0: float, kx0: float, ky0: float,

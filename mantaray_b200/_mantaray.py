@@ -71,12 +71,15 @@ def single_ray(x0: float, y0: float, kx0: float, ky0: float, duration: float, st
 
 
 def ray_tracing(x0, y0, kx0, ky0, duration: float, step_size: float,
-                bathymetry_filename: str, current_filename: str) -> RayBundle:
-    """src/ffi.rs:51-85.  ``t0 = 0`` (:72); inputs are zipped to the shortest (:65-70)."""
+                bathymetry_filename: str, current_filename: str, *, env: bool = False) -> RayBundle:
+    """src/ffi.rs:51-85.  ``t0 = 0`` (:72); inputs are zipped to the shortest (:65-70).
+
+    ``env=True`` (extension) also fills ``result.depth/u/v``: the columns of the reference's unfilled
+    ``Ray`` record (src/datatype.rs:165-194) at every stored row."""
     n = min(len(x0), len(y0), len(kx0), len(ky0))
     dev = _devices()
     if n < 4096:                         # not worth more than one device
         dev = dev[:1]
     with _capi.Fields.open_netcdf3(str(bathymetry_filename), str(current_filename), devices=dev) as f:
-        res = _capi.trace_many(f, x0, y0, kx0, ky0, 0.0, duration, step_size, math=MR_MATH_FAST, pinned=None)
+        res = _capi.trace_many(f, x0, y0, kx0, ky0, 0.0, duration, step_size, math=MR_MATH_FAST, pinned=None, env=env)
     return RayBundle(res)

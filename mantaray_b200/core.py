@@ -76,18 +76,32 @@ def single_ray(x0: float, y0: float, kx0: float, ky0: float, duration: float, st
     return _dataset({v: cols[i] for i, v in enumerate(_VARNAMES)}, ("time_step",))
 
 
-def ray_tracing(x0, y0, kx0, ky0, duration: float, step_size: float, bathymetry: str, current: str):
+def ray_tracing(x0, y0, kx0, ky0, duration: float, step_size: float, bathymetry: str, current: str, *,
+                diagnostics: bool = False):
     """Ray tracing for multiple initial conditions.
 
     Parameters and return value as ``mantaray.ray_tracing``
     (python/mantaray/core.py:68-132): variables ``time, x, y, kx, ky`` of shape
     ``(time_step, ray)``, every ray NaN-padded to the longest ray.
+
+    ``diagnostics=True`` (extension, off by default) adds the environment along the rays — ``depth``
+    (f32), ``u``, ``v``: the columns of the reference's ``Ray`` record, src/datatype.rs:165-194 — and
+    what the notebooks derive from it afterwards (notebooks/snells_law_verification.ipynb, cell 9):
+    ``k = |(kx, ky)|``, ``theta = atan2(ky, kx)`` and the intrinsic frequency
+    ``sigma = sqrt(g k tanh(k depth))`` with the solver's g = 9.8 (src/wave_ray_path.rs:23).
     """
-    bundle = _mantaray.ray_tracing(x0, y0, kx0, ky0, duration, step_size, str(bathymetry), str(current))
+    extra = {"env": True} if diagnostics else {}
+    bundle = _mantaray.ray_tracing(x0, y0, kx0, ky0, duration, step_size, str(bathymetry), str(current), **extra)
     r = bundle.result
     longest = int(r.rows.max()) if r.rows.size else 0
     step = np.arange(longest)
     # time of a row is ray-independent; a ray has it only for the rows it stored
     time = np.where(step[:, None] < r.rows[None, :], r.t[:longest, None], np.nan)
     data = {"time": time, "x": r.x[:longest], "y": r.y[:longest], "kx": r.kx[:longest], "ky": r.ky[:longest]}
+    if diagnostics:
+        kx, ky, depth = data["kx"], data["ky"], r.depth[:longest]
+        k = np.hypot(kx, ky)
+        with np.errstate(invalid="ignore"):
+            sigma = np.sqrt(9.8 * k * np.tanh(k * depth.astype(np.float64)))
+        data.update(depth=depth, u=r.u[:longest], v=r.v[:longest], k=k, theta=np.arctan2(ky, kx), sigma=sigma)
     return _dataset(data, ("time_step", "ray"), index={"time_step": step, "ray": np.arange(r.rows.size)})

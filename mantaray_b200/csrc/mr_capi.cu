@@ -380,6 +380,7 @@ struct HostJob {
     mr_trace_opts o;
     double *x, *y, *kx, *ky;
     int32_t *rows, *len; double *fin;
+    mr_env_planes env;           // depth/u/v planes at the stored rows, each may be NULL
 };
 
 struct DevBuf {
@@ -387,12 +388,15 @@ struct DevBuf {
     double *traj = nullptr;      // [4][rows_cap][chunk]
     int32_t *rows = nullptr, *len = nullptr;
     double *fin = nullptr;       // [4][chunk]
+    float *depth = nullptr;      // [rows_cap][chunk] environment planes (mr_trace_many_env)
+    double *u = nullptr, *v = nullptr;
     cudaEvent_t computed = nullptr, drained = nullptr;
 };
 
 static void free_devbuf(DevBuf &b)
 {
     cudaFree(b.ic); cudaFree(b.traj); cudaFree(b.rows); cudaFree(b.len); cudaFree(b.fin);
+    cudaFree(b.depth); cudaFree(b.u); cudaFree(b.v);
     if (b.computed) cudaEventDestroy(b.computed);
     if (b.drained) cudaEventDestroy(b.drained);
     b = DevBuf{};
@@ -430,7 +434,8 @@ static int trace_block_on_device(const DeviceFields &d, const HostJob &j, int64_
         size_t free_b = 0, total_b = 0;
         MR_TRY(cudaMemGetInfo(&free_b, &total_b));
         // bytes one ray needs on the device
-        const double per_ray = 32.0 + (want_traj ? 32.0 * (double)j.rows_cap : 0.0) + 8.0 + 32.0;
+        const double env_row = (j.env.depth ? 4.0 : 0.0) + (j.env.u ? 8.0 : 0.0) + (j.env.v ? 8.0 : 0.0);
+        const double per_ray = 32.0 + (want_traj ? (32.0 + env_row) * (double)j.rows_cap : 0.0) + 8.0 + 32.0;
         double budget = 0.80 * (double)free_b;
         if (j.o.chunk_rays > 0) {
             chunk = std::min<int64_t>(n, j.o.chunk_rays);
@@ -453,6 +458,9 @@ static int trace_block_on_device(const DeviceFields &d, const HostJob &j, int64_
         MR_TRY(cudaMalloc(&buf[b].rows, sizeof(int32_t) * (size_t)chunk));
         MR_TRY(cudaMalloc(&buf[b].len, sizeof(int32_t) * (size_t)chunk));
         if (j.fin) MR_TRY(cudaMalloc(&buf[b].fin, sizeof(double) * 4 * (size_t)chunk));
+        if (j.env.depth) MR_TRY(cudaMalloc(&buf[b].depth, sizeof(float) * (size_t)j.rows_cap * (size_t)chunk));
+        if (j.env.u) MR_TRY(cudaMalloc(&buf[b].u, sizeof(double) * (size_t)j.rows_cap * (size_t)chunk));
+        if (j.env.v) MR_TRY(cudaMalloc(&buf[b].v, sizeof(double) * (size_t)j.rows_cap * (size_t)chunk));
         MR_TRY(cudaEventCreateWithFlags(&buf[b].computed, cudaEventDisableTiming));
         MR_TRY(cudaEventCreateWithFlags(&buf[b].drained, cudaEventDisableTiming));
     }
@@ -480,8 +488,19 @@ static int trace_block_on_device(const DeviceFields &d, const HostJob &j, int64_
                 cudaError_t e = j.o.math == MR_MATH_STRICT ? launch_trace_strict(a, s_comp) : launch_trace_fast(a, s_comp);
                 if (e != cudaSuccess) { rc = bail(MR_ERR_CUDA, std::string("trace kernel launch: ") + cudaGetErrorString(e)); goto done; }
             }
+            if (B.depth || B.u || B.v)       // the fields at every stored state, from the planes just written
+                MR_TRY(launch_sample(d.b, d.c, j.rows_cap, m, chunk, tx, tx + plane, B.depth, B.u, B.v, s_comp));
             MR_TRY(cudaEventRecord(B.computed, s_comp));
             MR_TRY(cudaStreamWaitEvent(s_copy, B.computed, 0));
+            if (j.env.depth)
+                MR_TRY(cudaMemcpy2DAsync(j.env.depth + c0, sizeof(float) * (size_t)j.n_total, B.depth, sizeof(float) * (size_t)chunk,
+                                         sizeof(float) * (size_t)m, (size_t)j.rows_cap, cudaMemcpyDeviceToHost, s_copy));
+            if (j.env.u)
+                MR_TRY(cudaMemcpy2DAsync(j.env.u + c0, sizeof(double) * (size_t)j.n_total, B.u, sizeof(double) * (size_t)chunk,
+                                         sizeof(double) * (size_t)m, (size_t)j.rows_cap, cudaMemcpyDeviceToHost, s_copy));
+            if (j.env.v)
+                MR_TRY(cudaMemcpy2DAsync(j.env.v + c0, sizeof(double) * (size_t)j.n_total, B.v, sizeof(double) * (size_t)chunk,
+                                         sizeof(double) * (size_t)m, (size_t)j.rows_cap, cudaMemcpyDeviceToHost, s_copy));
             if (want_traj) {
                 double *dsts[4] = { j.x, j.y, j.kx, j.ky };
                 for (int f = 0; f < 4; ++f) {
@@ -647,6 +666,15 @@ int mr_trace_many(mr_fields *f, int64_t n,
                   double *t, double *x, double *y, double *kx, double *ky,
                   int32_t *rows, int32_t *len, double *final_state)
 {
+    return mr_trace_many_env(f, n, x0, y0, kx0, ky0, t0, t_end, dt, opts, t, x, y, kx, ky, rows, len, final_state, nullptr);
+}
+
+int mr_trace_many_env(mr_fields *f, int64_t n,
+                      const double *x0, const double *y0, const double *kx0, const double *ky0,
+                      double t0, double t_end, double dt, const mr_trace_opts *opts,
+                      double *t, double *x, double *y, double *kx, double *ky,
+                      int32_t *rows, int32_t *len, double *final_state, const mr_env_planes *env)
+{
     if (!f) return fail(MR_ERR_BAD_ARG, "mr_trace_many: NULL field handle");
     if (n < 0) return fail(MR_ERR_BAD_ARG, "mr_trace_many: n < 0");
     if (n > 0 && (!x0 || !y0 || !kx0 || !ky0)) return fail(MR_ERR_BAD_ARG, "mr_trace_many: NULL initial-condition array");
@@ -657,6 +685,8 @@ int mr_trace_many(mr_fields *f, int64_t n,
     if (nsteps < 0) return fail(MR_ERR_BAD_ARG, "mr_trace_many: need dt > 0 and 0 <= (t_end - t0)/dt < 2^31 (the reference panics here)");
     const bool any_traj = x || y || kx || ky;
     if (any_traj && !(x && y && kx && ky)) return fail(MR_ERR_BAD_ARG, "mr_trace_many: pass all four of x, y, kx, ky or none");
+    const bool any_env = env && (env->depth || env->u || env->v);
+    if (any_env && !any_traj) return fail(MR_ERR_BAD_ARG, "mr_trace_many_env: the environment planes need the x, y, kx, ky planes");
     fill_time(t, t0, dt, nsteps, o.stride);
     if (n == 0) return MR_OK;
 
@@ -664,6 +694,7 @@ int mr_trace_many(mr_fields *f, int64_t n,
     j.n_total = n; j.x0 = x0; j.y0 = y0; j.kx0 = kx0; j.ky0 = ky0;
     j.dt = dt; j.nsteps = nsteps; j.rows_cap = nsteps / o.stride + 1; j.o = o;
     j.x = x; j.y = y; j.kx = kx; j.ky = ky; j.rows = rows; j.len = len; j.fin = final_state;
+    j.env = any_env ? *env : mr_env_planes{nullptr, nullptr, nullptr};
 
     std::lock_guard<std::mutex> guard(f->mu);
     const int G = (int)f->devs.size();
@@ -747,6 +778,74 @@ int mr_trace_device(mr_fields *f, int device, void *stream, int64_t n,
     if (cur != device) cudaSetDevice(cur);
     if (rc == MR_OK && launches) *launches = 1;
     return rc;
+}
+
+int mr_sample_device(mr_fields *f, int device, void *stream, int64_t rows, int64_t n, int64_t ld,
+                     const double *d_x, const double *d_y,
+                     float *d_depth, double *d_u, double *d_v, int32_t *launches)
+{
+    if (launches) *launches = 0;
+    if (!f) return fail(MR_ERR_BAD_ARG, "mr_sample_device: NULL field handle");
+    const DeviceFields *d = find_device(f, device);
+    if (!d) return fail(MR_ERR_BAD_ARG, "mr_sample_device: device " + std::to_string(device) + " is not in the handle's mask");
+    if (rows < 0 || n < 0 || ld < n) return fail(MR_ERR_BAD_ARG, "mr_sample_device: need rows >= 0 and 0 <= n <= ld");
+    if (rows == 0 || n == 0 || !(d_depth || d_u || d_v)) return MR_OK;
+    if (!d_x || !d_y) return fail(MR_ERR_BAD_ARG, "mr_sample_device: NULL point array");
+    int cur = -1;
+    MR_CUDA(cudaGetDevice(&cur));
+    if (cur != device) MR_CUDA(cudaSetDevice(device));
+    cudaError_t e = launch_sample(d->b, d->c, rows, n, ld, d_x, d_y, d_depth, d_u, d_v, (cudaStream_t)stream);
+    if (cur != device) cudaSetDevice(cur);
+    if (e != cudaSuccess) return fail(MR_ERR_CUDA, std::string("sample kernel launch: ") + cudaGetErrorString(e));
+    if (launches) *launches = 1;
+    return MR_OK;
+}
+
+int mr_sample_fields(mr_fields *f, int64_t count, const double *x, const double *y,
+                     float *depth, double *u, double *v)
+{
+    if (!f) return fail(MR_ERR_BAD_ARG, "mr_sample_fields: NULL field handle");
+    if (count < 0) return fail(MR_ERR_BAD_ARG, "mr_sample_fields: count < 0");
+    if (count == 0 || !(depth || u || v)) return MR_OK;
+    if (!x || !y) return fail(MR_ERR_BAD_ARG, "mr_sample_fields: NULL point array");
+    std::lock_guard<std::mutex> guard(f->mu);
+    const DeviceFields &d = f->devs[0];
+    MR_CUDA(cudaSetDevice(d.dev));
+    // slabs bound the device footprint (36 B a point) whatever `count` is
+    const int64_t slab = std::min<int64_t>(count, (int64_t)1 << 26);
+    double *dx = nullptr, *dy = nullptr, *du = nullptr, *dv = nullptr;
+    float *dh = nullptr;
+    int rc = MR_OK;
+    auto release = [&] { cudaFree(dx); cudaFree(dy); cudaFree(du); cudaFree(dv); cudaFree(dh); };
+#define MR_TRY(call)                                                                              \
+    do {                                                                                          \
+        cudaError_t e__ = (call);                                                                 \
+        if (e__ != cudaSuccess) {                                                                 \
+            rc = fail(e__ == cudaErrorMemoryAllocation ? MR_ERR_OOM : MR_ERR_CUDA,                \
+                      std::string(#call) + ": " + cudaGetErrorString(e__));                       \
+            cudaDeviceSynchronize(); (void)cudaGetLastError();                                    \
+            release();                                                                            \
+            return rc;                                                                            \
+        }                                                                                         \
+    } while (0)
+    MR_TRY(cudaMalloc(&dx, sizeof(double) * (size_t)slab));
+    MR_TRY(cudaMalloc(&dy, sizeof(double) * (size_t)slab));
+    if (depth) MR_TRY(cudaMalloc(&dh, sizeof(float) * (size_t)slab));
+    if (u) MR_TRY(cudaMalloc(&du, sizeof(double) * (size_t)slab));
+    if (v) MR_TRY(cudaMalloc(&dv, sizeof(double) * (size_t)slab));
+    for (int64_t c0 = 0; c0 < count; c0 += slab) {
+        const int64_t m = std::min(slab, count - c0);
+        MR_TRY(cudaMemcpyAsync(dx, x + c0, sizeof(double) * (size_t)m, cudaMemcpyHostToDevice, 0));
+        MR_TRY(cudaMemcpyAsync(dy, y + c0, sizeof(double) * (size_t)m, cudaMemcpyHostToDevice, 0));
+        MR_TRY(launch_sample(d.b, d.c, 1, m, m, dx, dy, dh, du, dv, 0));
+        if (depth) MR_TRY(cudaMemcpyAsync(depth + c0, dh, sizeof(float) * (size_t)m, cudaMemcpyDeviceToHost, 0));
+        if (u) MR_TRY(cudaMemcpyAsync(u + c0, du, sizeof(double) * (size_t)m, cudaMemcpyDeviceToHost, 0));
+        if (v) MR_TRY(cudaMemcpyAsync(v + c0, dv, sizeof(double) * (size_t)m, cudaMemcpyDeviceToHost, 0));
+        MR_TRY(cudaStreamSynchronize(0));
+    }
+#undef MR_TRY
+    release();
+    return MR_OK;
 }
 
 int mr_measure_fp64_peak(int device, int millis, double *tflops)

@@ -371,6 +371,40 @@ int orc_current_and_gradient(const mr_current_desc *cu, double x, double y,
     return 0;
 }
 
+/* CurrentData::current for every kind; 0 = Ok, 1 = Err.
+ * constant_current.rs:51-53 (the point is ignored); cartesian_current.rs:448-467 */
+int orc_current(const mr_current_desc *cu, double x, double y, double *u, double *v)
+{
+    if (cu->kind == MR_CURRENT_CONSTANT) { *u = cu->u0; *v = cu->v0; return 0; }
+    if (cu->kind != MR_CURRENT_GRID) return 1;
+    size_t c[4][2];
+    if (orc_current_four_corners(cu, x, y, c)) return 1;                        /* :450-453 */
+    float uf, vf;
+    if (current_interpolate(cu, c, (float)x, (float)y, cu->u, &uf)) return 1;   /* :456-460 */
+    if (current_interpolate(cu, c, (float)x, (float)y, cu->v, &vf)) return 1;   /* :461-465 */
+    *u = (double)uf; *v = (double)vf;                                           /* :467 */
+    return 0;
+}
+
+/* depth() at (x as f32, y as f32) (wave_ray_path.rs:122) and current() at (x, y) for `count` points:
+ * the depth and current columns of Ray{time,state,depth,current}, datatype.rs:165-194.  Err -> NaN. */
+void orc_sample_fields(const mr_bathymetry_desc *b, const mr_current_desc *cu, int64_t count,
+                       const double *x, const double *y, float *depth, double *u, double *v)
+{
+    for (int64_t i = 0; i < count; ++i) {
+        if (depth) {
+            float h;
+            depth[i] = orc_depth(b, (float)x[i], (float)y[i], &h) ? NAN : h;
+        }
+        if (u || v) {
+            double uu, vv;
+            if (orc_current(cu, x[i], y[i], &uu, &vv)) uu = vv = NAN;
+            if (u) u[i] = uu;
+            if (v) v[i] = vv;
+        }
+    }
+}
+
 /* ------------------------------------------------------------------------- */
 /* WaveRayPath — src/wave_ray_path.rs                                         */
 /* ------------------------------------------------------------------------- */

@@ -25,6 +25,9 @@ int  orc_depth_and_gradient(const mr_bathymetry_desc *b, float x, float y, float
 /* src/current/cartesian_current.rs:231-253, 283-339, 487-542 */
 int  orc_current_nearest(double target, const double *arr, int n, double *index);
 int  orc_current_four_corners(const mr_current_desc *cu, double x, double y, size_t c[4][2]);
+int  orc_current(const mr_current_desc *cu, double x, double y, double *u, double *v);
+void orc_sample_fields(const mr_bathymetry_desc *b, const mr_current_desc *cu, int64_t count,
+                       const double *x, const double *y, float *depth, double *u, double *v);
 int  orc_current_and_gradient(const mr_current_desc *cu, double x, double y, double *u, double *v, double grad[4]);
 
 /* src/wave_ray_path.rs:118-247 */

@@ -45,6 +45,9 @@ def load() -> C.CDLL:
     lib.orc_current_nearest.argtypes = [C.c_double, C.c_void_p, C.c_int, f64p]
     lib.orc_current_four_corners.argtypes = [Cu, C.c_double, C.c_double, C.POINTER(C.c_size_t * 2 * 4)]
     lib.orc_current_and_gradient.argtypes = [Cu, C.c_double, C.c_double, f64p, f64p, C.POINTER(C.c_double * 4)]
+    lib.orc_current.argtypes = [Cu, C.c_double, C.c_double, f64p, f64p]
+    lib.orc_sample_fields.argtypes = [B, Cu, C.c_int64] + [C.c_void_p] * 5
+    lib.orc_sample_fields.restype = None
     lib.orc_group_velocity.argtypes = [C.c_double, C.c_double, f64p]
     lib.orc_dkdt_bathy.argtypes = [C.c_double] * 4 + [f64p, f64p]
     lib.orc_dkdt_bathy.restype = None
@@ -129,6 +132,26 @@ def current_and_gradient(current, x, y):
     if load().orc_current_and_gradient(C.byref(d), float(x), float(y), C.byref(u), C.byref(v), C.byref(g)):
         raise Err("current_and_gradient")
     return (u.value, v.value), ((g[0], g[1]), (g[2], g[3]))
+
+
+def current(current, x, y):
+    d = current.to_desc()
+    u, v = C.c_double(), C.c_double()
+    if load().orc_current(C.byref(d), float(x), float(y), C.byref(u), C.byref(v)):
+        raise Err("current")
+    return u.value, v.value
+
+
+def sample_fields(bathy, current, x, y):
+    """``(depth f32, u, v)`` at points: ``depth()`` / ``current()``, NaN where they return Err."""
+    bd, cd = bathy.to_desc(), current.to_desc()
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    depth = np.empty(x.shape, dtype=np.float32)
+    u, v = np.empty(x.shape), np.empty(x.shape)
+    load().orc_sample_fields(C.byref(bd), C.byref(cd), x.size, x.ctypes.data, y.ctypes.data,
+                             depth.ctypes.data, u.ctypes.data, v.ctypes.data)
+    return depth, u, v
 
 
 def group_velocity(k, h) -> float:

@@ -94,6 +94,26 @@ def test_analytic_fields(oracle, gpu, bathy, cur, math):
 
 
 @pytest.mark.parametrize("math", MODES)
+@pytest.mark.parametrize("bathy", [
+    ConstantDepth(10.0), ConstantSlope(50.0, 10.0, -5.0, 0.02, -0.03), ArrayDepth(np.arange(1.0, 1601.0).reshape(40, 40)),
+], ids=["constant", "slope", "array"])
+def test_special_inputs_analytic(oracle, gpu, bathy, math):
+    """NaN / inf / negative / huge start coordinates on the analytic kinds.  ArrayDepth indexes with a
+    saturating cast (array_depth.rs:19-20: NaN -> 0, negative -> 0), so a ray with a NaN x keeps a finite
+    depth and wavenumber derivative and keeps integrating with x = NaN: `rows` tells that apart from a stop."""
+    x0 = np.array([np.nan, 3.0, -4.0, 5.0, 1e30, np.inf, 2.5, 39.9, 41.0, 0.0])
+    y0 = np.array([2.0, np.nan, 3.0, -2.0, 1.0, 1.0, -np.inf, 39.9, 1.0, 0.0])
+    n = x0.size
+    rays = (x0, y0, np.full(n, 0.05), np.full(n, 0.02))
+    res, ref = run_both(oracle, gpu, bathy, ConstantCurrent(0.1, 0.0), rays, 0.0, 30.0, 0.5, math)
+    assert_parity(res, ref, what="special analytic")
+    assert np.array_equal(res.rows, ref.rows)
+    if isinstance(bathy, ArrayDepth):
+        assert ref.rows[0] > 3 and ref.len[0] == 0          # NaN x: integrates on (until y leaves the array), never NaN-free
+        assert ref.rows[8] == 2                              # x = 41 is outside the 40 x 40 array: NaN depth
+
+
+@pytest.mark.parametrize("math", MODES)
 def test_special_inputs(oracle, gpu, math):
     """NaN / zero-k / out-of-domain starts / inf, on gridded fields."""
     wl = W.c2_sea_mount(8, 50, half=100)

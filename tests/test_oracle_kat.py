@@ -329,3 +329,44 @@ def test_core_cases_on_oracle(oracle):
     # variable length: the ray heading to -x leaves the 20 km domain first (test_core.py:81-101)
     r = oracle.trace_many(bathy, cur, 2 * [-1e3], 2 * [0], [-0.01, 0.01], 2 * [0], 0.0, 1e6, 20.0)
     assert r.rows[0] < r.rows[1] < 50_001
+
+
+# ---- depth() / current(): the environment columns of Ray{time,state,depth,current} (datatype.rs:165-194) --
+def test_sample_fields_matches_the_accessors(oracle):
+    O = oracle
+    """orc_sample_fields is orc_depth / orc_current point by point, Err -> NaN; current() returns the (u, v)
+    of current_and_gradient (cartesian_current.rs:448-467 against :487-542)"""
+    rng = np.random.default_rng(3)
+    x = (500.0 * np.arange(101)).astype(np.float32)
+    y = (500.0 * np.arange(51)).astype(np.float32)
+    X, Y = np.meshgrid(x.astype(np.float64), y.astype(np.float64))
+    bathy = CartesianNetcdf3(x, y, 0.05 * X + 0.01 * Y)
+    cur = CartesianCurrent(x.astype(np.float64), y.astype(np.float64), 1e-4 * X, -2e-4 * Y)
+    px = rng.uniform(-5_000.0, 55_000.0, 400)
+    py = rng.uniform(-5_000.0, 30_000.0, 400)
+    px[:4] = [np.nan, 0.0, 50_000.0, 25_000.0]
+    py[:4] = [10.0, 0.0, 25_000.0, np.nan]
+    depth, u, v = O.sample_fields(bathy, cur, px, py)
+    assert depth.dtype == np.float32
+    n_err = 0
+    for i in range(px.size):
+        try:
+            h = O.depth(bathy, px[i], py[i])
+        except O.Err:
+            h = np.nan
+        assert (np.isnan(h) and np.isnan(depth[i])) or np.float32(h) == depth[i]
+        try:
+            uu, vv = O.current(cur, px[i], py[i])
+            (u2, v2), _ = O.current_and_gradient(cur, px[i], py[i])
+            assert (uu, vv) == (u2, v2)
+        except O.Err:
+            uu = vv = np.nan
+            n_err += 1
+        assert (np.isnan(uu) and np.isnan(u[i])) or (uu == u[i] and vv == v[i])
+    assert 0 < n_err < px.size
+    # constant kinds: depth is NaN for a NaN point (constant_depth.rs:26-32), the current ignores it (:51-53)
+    depth, u, v = O.sample_fields(ConstantDepth(12.0), ConstantCurrent(0.3, -0.1), [1.0, np.nan], [2.0, 0.0])
+    assert depth[0] == 12.0 and np.isnan(depth[1]) and (u == 0.3).all() and (v == -0.1).all()
+    # quadrant depths of cartesian_netcdf3.rs:663-689 through the batch entry point
+    d2, _, _ = O.sample_fields(bathy, ConstantCurrent(0, 0), [10_000.0, 30_000.0], [5_000.0, 20_000.0])
+    np.testing.assert_allclose(d2, [0.05 * 10_000 + 0.01 * 5_000, 0.05 * 30_000 + 0.01 * 20_000], rtol=1e-6)

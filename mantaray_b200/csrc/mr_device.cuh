@@ -459,7 +459,9 @@ __device__ __forceinline__ void rhs_f64_fast(double kx, double ky, double k, dou
                                              const CurrentVal &cv, double out[4])
 {
     const double kh = k * h;
-    double T = 1.0, hs2 = 0.0, csch_sech = 0.0;      // tanh kh, kh/cosh^2 kh, 1/(sinh kh cosh kh)
+    // tanh kh, kh/cosh^2 kh, 1/(sinh kh cosh kh).  kh * 0 is 0 — or NaN for h = +inf, where the reference's
+    // kh/sinh(2kh) is inf/inf: cg is NaN there while the bathymetric term stays -0 * grad(h), as below
+    double T = 1.0, hs2 = kh * 0.0, csch_sech = 0.0;
     // Deep water, kh >= 22: exp(-2kh) < 8e-20, so in f64 tanh kh == 1 exactly, kh/cosh^2 kh <
     // 2^-57 vanishes against it, and the bathymetric term changes k by less than 3e-18 of itself
     // per step — below half an ulp, i.e. the reference's own sum rounds it away.  The
@@ -664,11 +666,7 @@ struct FastRay {
         }
         // h <= 0 -> cg = NaN and the bathymetric term is NaN too (inf*0 or sqrt of a negative);
         // k == 0 -> Err (wave_ray_path.rs:178-183): all four NaN, like a failed lookup
-        // h == +inf -> cg = NaN (inf/inf in wave_ray_path.rs:184-186) and the stage after it sees a NaN
-        // position: the step's new state is all-NaN either way
-        // (the test on h goes through h + h * -0: that is h for a finite h and NaN for +inf, one FFMA instead of
-        // a second compare — measured 0.7 % of the C4 step)
-        ok = ok && __fmaf_rn(h32, -0.0f, h32) > 0.0f && k2 > 0.0;
+        ok = ok && h32 > 0.0f && k2 > 0.0;
         const double h = ok ? (double)h32 : qnan();
         rhs_f64_fast(kx, ky, k, cs, sn, h, dhdx, dhdy, cv, out);
     }

@@ -114,6 +114,33 @@ def test_special_inputs_analytic(oracle, gpu, bathy, math):
 
 
 @pytest.mark.parametrize("math", MODES)
+def test_infinite_depth_nodes(oracle, gpu, math):
+    """grid nodes holding +inf / -inf / NaN: cells touching them give a non-finite depth or gradient; rays that
+    run into them stop where the reference stops them, with the same rows"""
+    x = (100.0 * np.arange(40)).astype(np.float32)
+    y = (100.0 * np.arange(30)).astype(np.float32)
+    depth = np.full((30, 40), 200.0)
+    depth[10, 12] = np.inf
+    depth[20, 25] = -np.inf
+    depth[5, 30] = np.nan
+    depth[15:18, 20:23] = np.inf            # a whole block: inf - inf gradients
+    cx = 100.0 * np.arange(40.0)
+    cy = 100.0 * np.arange(30.0)
+    cur = CartesianCurrent(cx, cy, np.full((30, 40), 0.2), np.full((30, 40), -0.1))
+    bathy = CartesianNetcdf3(x, y, depth)
+    n = 600
+    rng = np.random.default_rng(11)
+    th = rng.uniform(-0.5, 0.5, n)
+    rays = (np.full(n, 150.0), np.linspace(150.0, 2750.0, n), 0.05 * np.cos(th), 0.05 * np.sin(th))
+    res, ref = run_both(oracle, gpu, bathy, cur, rays, 0.0, 600.0, 2.0, math)
+    assert_parity(res, ref, what="non-finite nodes")
+    assert np.array_equal(res.rows, ref.rows)
+    assert ref.rows.min() < 100 and ref.rows.max() > 250
+    # rays whose last rows are partially NaN (cg = NaN from an infinite depth, wavenumber still finite)
+    assert (ref.rows - ref.len >= 2).sum() > 5
+
+
+@pytest.mark.parametrize("math", MODES)
 def test_special_inputs(oracle, gpu, math):
     """NaN / zero-k / out-of-domain starts / inf, on gridded fields."""
     wl = W.c2_sea_mount(8, 50, half=100)

@@ -205,7 +205,10 @@ __global__ void build_current_cells(const double *u, const double *v, int nx, in
 }
 
 // Are the f32 coordinates exactly affine, i.e. does the kernel's own arithmetic
-// (xa = fmaf(i, d, c[0]); xb = xa + d) reproduce every c[i] bit for bit?
+// (xa = fmaf(i, d, c[0]); xb = xa + d) reproduce every c[i] bit for bit, AND is every cell exactly d wide
+// in f32 (the reference forms dx = x2 - x1 per cell, interpolator.rs:62-63; the affine path replaces it by
+// the launch constant d)?  A non-representable origin passes the first test and fails the second: its
+// coordinates round differently from binade to binade (found by tests/test_gpu_fuzz.py).
 static bool affine_f32(const float *c, int n, float *d_out)
 {
     const float d = c[1] - c[0];
@@ -213,7 +216,11 @@ static bool affine_f32(const float *c, int n, float *d_out)
     for (int i = 0; i < n; ++i) {
         const float xa = std::fmaf((float)i, d, c[0]);
         if (xa != c[i]) return false;
-        if (i + 1 < n && xa + d != c[i + 1]) return false;
+        if (i + 1 < n) {
+            volatile float xb = xa + d;
+            volatile float w = xb - xa;
+            if (xb != c[i + 1] || w != d) return false;
+        }
     }
     *d_out = d;
     return true;

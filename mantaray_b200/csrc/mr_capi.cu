@@ -289,8 +289,10 @@ static int upload_fields(DeviceFields &d, const mr_bathymetry_desc *b, const mr_
             std::memcpy(&a, &lo, 4); std::memcpy(&b2, &hi, 4);
             return (unsigned long long)a | ((unsigned long long)b2 << 32);
         };
-        B.uniform = affine_f32(b->x, b->nx, &B.dxf) && affine_f32(b->y, b->ny, &B.dyf) &&
-                    basis_coeffs(B.dxf, B.dyf, &B.c01, &B.c10) && recip_ok(B.sx, &B.rsx) && recip_ok(B.sy, &B.rsy);
+        B.fastdiv = recip_ok(B.sx, &B.rsx) && recip_ok(B.sy, &B.rsy);
+        if (!B.fastdiv) B.rsx = B.rsy = 0.0f;
+        B.uniform = B.fastdiv && affine_f32(b->x, b->nx, &B.dxf) && affine_f32(b->y, b->ny, &B.dyf) &&
+                    basis_coeffs(B.dxf, B.dyf, &B.c01, &B.c10);
         B.p0 = pack2(B.xf0, B.yf0); B.rs2 = pack2(B.rsx, B.rsy); B.ns2 = pack2(-B.sx, -B.sy);
         B.d2 = pack2(B.dxf, B.dyf); B.c2 = pack2(B.c10, B.c01);
     } else if (b->kind == MR_BATHY_ARRAY) {

@@ -44,6 +44,7 @@ struct BathyDev {
     float  xf0, yf0;           // x[0], y[0]
     float  sx, sy;             // |x[1]-x[0]|, |y[1]-y[0]| in f32   (cartesian_netcdf3.rs:287)
     float  rsx, rsy;           // RN(1/sx), RN(1/sy); 0 when the exact-division shortcut does not apply
+    int32_t fastdiv;           // fdiv_const(., sx, rsx) and (., sy, rsy) are usable (affine grid or not)
     double x_space, y_space;   // x[1]-x[0] in f64 of the f32 values (cartesian_netcdf3.rs:119-120)
     // per-cell records for the fast path: cell (x1,y1), x1 < nx-1, y1 < ny-1, 32 bytes each:
     //   float4 {z_sw, a10, a01, a11} (bilinear_coeffs of the corner depths as f32), double2 {dhdx, dhdy} (the f32 gradient of
@@ -532,6 +533,9 @@ struct FastRay {
                 q = fma2(fma2(q, b.ns2, t), b.rs2, q);
                 q = fma2(fma2(q, b.ns2, t), b.rs2, q);
                 ix = lo_of(q); iy = hi_of(q);
+            } else if (b.fastdiv) {     // the index divides by the constant |x[1]-x[0]| whatever the other spacings are
+                ix = fdiv_const(__fsub_rn(xf, b.xf0), b.sx, b.rsx);
+                iy = fdiv_const(__fsub_rn(yf, b.yf0), b.sy, b.rsy);
             } else {
                 ix = __fdiv_rn(__fsub_rn(xf, b.xf0), b.sx);
                 iy = __fdiv_rn(__fsub_rn(yf, b.yf0), b.sy);

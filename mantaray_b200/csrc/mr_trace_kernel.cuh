@@ -50,6 +50,10 @@ static constexpr int kBlock = kBlockThreads;
 #ifndef MR_MIN_BLOCKS
 #define MR_MIN_BLOCKS 7
 #endif
+// grids whose f32 coordinates are not affine keep the per-cell corner coordinates and basis live: more registers
+#ifndef MR_MIN_BLOCKS_GENERIC
+#define MR_MIN_BLOCKS_GENERIC 5
+#endif
 #ifndef MR_MIN_BLOCKS_NR2
 #define MR_MIN_BLOCKS_NR2 4
 #endif
@@ -89,7 +93,7 @@ __device__ __forceinline__ void store_row(const TraceArgs &a, int64_t o, const d
 // NR rays per thread (adjacent rays i0, i0+1): the RHS phases of the rays interleave (mr_device.cuh,
 // rhs_fast_n), per-thread uniform work is shared, and rows are stored 16 bytes at a time.
 template <int BK, int CK, int MATH, bool UNI, int NR>
-__global__ void __launch_bounds__(kBlock, (MATH == MR_MATH_FAST) ? (NR == 2 ? MR_MIN_BLOCKS_NR2 : MR_MIN_BLOCKS) : 1)
+__global__ void __launch_bounds__(kBlock, (MATH == MR_MATH_FAST) ? (NR == 2 ? MR_MIN_BLOCKS_NR2 : (UNI ? MR_MIN_BLOCKS : MR_MIN_BLOCKS_GENERIC)) : 1)
 trace_kernel(const __grid_constant__ TraceArgs a)
 {
     const int64_t i0 = ((int64_t)blockIdx.x * kBlock + threadIdx.x) * NR;

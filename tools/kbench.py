@@ -28,6 +28,13 @@ def child(lib_path, rays, steps, workload, math, notraj=False, nx=2048):
         wl.bathymetry = ConstantDepth(4000.0) if mode in ("deep", "deepcur") else ConstantSlope(300.0, 0.0, 0.0, -1e-4, -1e-4)
         if mode in ("deep", "slope"):
             wl.current = ConstantCurrent(0.1, -0.05)
+    if os.environ.get("KB_SHIFT"):         # same fields on coordinates with a non-representable origin:
+        from mantaray_b200 import CartesianNetcdf3, CartesianCurrent   # the f32 grids are then not affine
+        sh = float(os.environ["KB_SHIFT"])
+        b, c = wl.bathymetry, wl.current
+        wl.bathymetry = CartesianNetcdf3(np.asarray(b.x, np.float64) + sh, np.asarray(b.y, np.float64) + sh, b.depth)
+        wl.current = CartesianCurrent(c.x + sh, c.y + sh, c.u, c.v)
+        x0, y0 = x0 + sh, y0 + sh
     dev = torch.device("cuda", 0)
     f = _capi.Fields(wl.bathymetry, wl.current, devices=[0])
     ic = torch.from_numpy(np.stack([x0, y0, kx0, ky0])).to(dev)

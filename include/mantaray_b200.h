@@ -152,6 +152,12 @@ void mr_fields_free(mr_fields *f);
 /* Devices the handle lives on, as a bit mask. */
 uint32_t mr_fields_device_mask(const mr_fields *f);
 
+/* The host-buffer entry points (mr_trace_many, mr_trace_many_env, mr_single_ray)
+ * keep their device work buffers in the handle so that the next call does not
+ * allocate again: up to two slabs of <= 16 GB per device.  This gives them back
+ * to the device now; mr_fields_free does so too. */
+void mr_fields_trim(mr_fields *f);
+
 /* ---- sizes --------------------------------------------------------------- */
 
 /* Number of RK4 steps the stepper takes: ceil((t_end - t0)/dt)

@@ -99,6 +99,7 @@ SIGNATURES = {
     "mr_fields_open_netcdf3": (C.c_int, [C.c_char_p, C.c_char_p, C.c_uint32, C.POINTER(C.c_void_p)]),
     "mr_fields_free": (None, [C.c_void_p]),
     "mr_fields_device_mask": (C.c_uint32, [C.c_void_p]),
+    "mr_fields_trim": (None, [C.c_void_p]),
     "mr_num_steps": (C.c_int64, [C.c_double, C.c_double, C.c_double]),
     "mr_num_rows": (C.c_int64, [C.c_double, C.c_double, C.c_double, C.c_int32]),
     "mr_trace_many": (

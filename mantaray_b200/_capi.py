@@ -185,6 +185,11 @@ class Fields:
     def device_mask(self) -> int:
         return int(self._lib.mr_fields_device_mask(self.handle))
 
+    def trim(self) -> None:
+        """Give the cached device work buffers of the host-buffer path back (``mr_fields_trim``)."""
+        if self._h:
+            load().mr_fields_trim(self._h)
+
     def free(self) -> None:
         if getattr(self, "_h", None):
             self._lib.mr_fields_free(self._h)

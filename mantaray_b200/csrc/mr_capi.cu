@@ -13,6 +13,9 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <memory>
@@ -88,11 +91,22 @@ __global__ void fdiv_selftest_kernel(float s, float r, unsigned long long *bad)
 }
 
 // ---- field handle -----------------------------------------------------------
+// Work memory of the host-buffer path (mr_trace_many), kept by the handle between calls: allocating and
+// freeing two ~16 GB slabs cost 20-480 ms per call on B200 (MR_DEBUG_TIMING), against 1.26 s of drain.
+struct WorkArea {
+    void *arena[2] = {nullptr, nullptr};
+    size_t bytes[2] = {0, 0};
+    cudaStream_t s_comp = nullptr, s_copy = nullptr;
+    cudaEvent_t computed[2] = {nullptr, nullptr}, drained[2] = {nullptr, nullptr};
+    size_t held() const { return bytes[0] + bytes[1]; }
+};
+
 struct DeviceFields {
     int dev = -1;
     BathyDev b{};
     CurrentDev c{};
     std::vector<void *> allocs;
+    WorkArea work;             // guarded by mr_fields::mu
 };
 
 }  // namespace mr
@@ -339,8 +353,30 @@ static int upload_fields(DeviceFields &d, const mr_bathymetry_desc *b, const mr_
     return MR_OK;
 }
 
+static void release_work(DeviceFields &d, bool everything)
+{
+    WorkArea &w = d.work;
+    if (d.dev < 0) return;
+    if (!w.arena[0] && !w.arena[1] && !w.s_comp) return;
+    cudaSetDevice(d.dev);
+    for (int b = 0; b < 2; ++b) {
+        cudaFree(w.arena[b]);
+        w.arena[b] = nullptr; w.bytes[b] = 0;
+    }
+    if (!everything) return;
+    for (int b = 0; b < 2; ++b) {
+        if (w.computed[b]) cudaEventDestroy(w.computed[b]);
+        if (w.drained[b]) cudaEventDestroy(w.drained[b]);
+        w.computed[b] = w.drained[b] = nullptr;
+    }
+    if (w.s_comp) cudaStreamDestroy(w.s_comp);
+    if (w.s_copy) cudaStreamDestroy(w.s_copy);
+    w.s_comp = w.s_copy = nullptr;
+}
+
 static void free_device_fields(DeviceFields &d)
 {
+    release_work(d, true);
     if (d.dev >= 0 && !d.allocs.empty()) {
         cudaSetDevice(d.dev);
         for (void *p : d.allocs) cudaFree(p);
@@ -402,19 +438,33 @@ struct DevBuf {
     cudaEvent_t computed = nullptr, drained = nullptr;
 };
 
-static void free_devbuf(DevBuf &b)
+// Lays the arrays of one slab buffer out in an arena (256-byte aligned each); with base == nullptr it only
+// measures.  Returns the bytes used.
+static size_t carve(DevBuf &B, char *base, int64_t chunk, int64_t rows_cap, bool traj, bool fin, const mr_env_planes &env)
 {
-    cudaFree(b.ic); cudaFree(b.traj); cudaFree(b.rows); cudaFree(b.len); cudaFree(b.fin);
-    cudaFree(b.depth); cudaFree(b.u); cudaFree(b.v);
-    if (b.computed) cudaEventDestroy(b.computed);
-    if (b.drained) cudaEventDestroy(b.drained);
-    b = DevBuf{};
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        char *p = base ? base + off : nullptr;
+        off += (bytes + 255) / 256 * 256;
+        return p;
+    };
+    const size_t c = (size_t)chunk, plane = (size_t)rows_cap * c;
+    B.ic = (double *)take(sizeof(double) * 4 * c);
+    B.traj = traj ? (double *)take(sizeof(double) * 4 * plane) : nullptr;
+    B.rows = (int32_t *)take(sizeof(int32_t) * c);
+    B.len = (int32_t *)take(sizeof(int32_t) * c);
+    B.fin = fin ? (double *)take(sizeof(double) * 4 * c) : nullptr;
+    B.depth = env.depth ? (float *)take(sizeof(float) * plane) : nullptr;
+    B.u = env.u ? (double *)take(sizeof(double) * plane) : nullptr;
+    B.v = env.v ? (double *)take(sizeof(double) * plane) : nullptr;
+    return off;
 }
 
 // Traces rays [lo, hi) on device d.  Rays are cut into slabs of `chunk` rays;
 // slab k+1 integrates on the compute stream while slab k drains to the host on
-// the copy stream (two device buffers).
-static int trace_block_on_device(const DeviceFields &d, const HostJob &j, int64_t lo, int64_t hi, std::string &err)
+// the copy stream (two device buffers).  Buffers, streams and events live in the
+// handle's WorkArea and are reused by the next call.
+static int trace_block_on_device(DeviceFields &d, const HostJob &j, int64_t lo, int64_t hi, std::string &err)
 {
     auto bail = [&](int code, const std::string &m) { err = m; return code; };
 #define MR_TRY(call)                                                                      \
@@ -430,8 +480,13 @@ static int trace_block_on_device(const DeviceFields &d, const HostJob &j, int64_
     int rc = MR_OK;
     const int64_t n = hi - lo;
     if (n <= 0) return MR_OK;
+    // MR_DEBUG_TIMING=1: where a host-buffer call spends its wall time (stderr)
+    static const bool timing = std::getenv("MR_DEBUG_TIMING") != nullptr;
+    using clk = std::chrono::steady_clock;
+    const auto t_begin = clk::now();
+    auto t_alloc = t_begin, t_enqueued = t_begin, t_synced = t_begin;
     const bool want_traj = j.x || j.y || j.kx || j.ky;
-    cudaStream_t s_comp = nullptr, s_copy = nullptr;
+    WorkArea &w = d.work;
     DevBuf buf[2];
     int nbuf = 1;
     int64_t chunk = n;
@@ -445,7 +500,7 @@ static int trace_block_on_device(const DeviceFields &d, const HostJob &j, int64_
         // bytes one ray needs on the device
         const double env_row = (j.env.depth ? 4.0 : 0.0) + (j.env.u ? 8.0 : 0.0) + (j.env.v ? 8.0 : 0.0);
         const double per_ray = 32.0 + (want_traj ? (32.0 + env_row) * (double)j.rows_cap : 0.0) + 8.0 + 32.0;
-        double budget = 0.80 * (double)free_b;
+        double budget = 0.80 * (double)(free_b + w.held());      // what this handle already holds is ours to reuse
         if (j.o.chunk_rays > 0) {
             chunk = std::min<int64_t>(n, j.o.chunk_rays);
         } else if (per_ray * (double)n > budget || (want_traj && per_ray * (double)n > 4e9)) {
@@ -459,21 +514,34 @@ static int trace_block_on_device(const DeviceFields &d, const HostJob &j, int64_
         }
         nbuf = chunk < n ? 2 : 1;
     }
-    MR_TRY(cudaStreamCreateWithFlags(&s_comp, cudaStreamNonBlocking));
-    MR_TRY(cudaStreamCreateWithFlags(&s_copy, cudaStreamNonBlocking));
-    for (int b = 0; b < nbuf; ++b) {
-        MR_TRY(cudaMalloc(&buf[b].ic, sizeof(double) * 4 * (size_t)chunk));
-        if (want_traj) MR_TRY(cudaMalloc(&buf[b].traj, sizeof(double) * 4 * (size_t)j.rows_cap * (size_t)chunk));
-        MR_TRY(cudaMalloc(&buf[b].rows, sizeof(int32_t) * (size_t)chunk));
-        MR_TRY(cudaMalloc(&buf[b].len, sizeof(int32_t) * (size_t)chunk));
-        if (j.fin) MR_TRY(cudaMalloc(&buf[b].fin, sizeof(double) * 4 * (size_t)chunk));
-        if (j.env.depth) MR_TRY(cudaMalloc(&buf[b].depth, sizeof(float) * (size_t)j.rows_cap * (size_t)chunk));
-        if (j.env.u) MR_TRY(cudaMalloc(&buf[b].u, sizeof(double) * (size_t)j.rows_cap * (size_t)chunk));
-        if (j.env.v) MR_TRY(cudaMalloc(&buf[b].v, sizeof(double) * (size_t)j.rows_cap * (size_t)chunk));
-        MR_TRY(cudaEventCreateWithFlags(&buf[b].computed, cudaEventDisableTiming));
-        MR_TRY(cudaEventCreateWithFlags(&buf[b].drained, cudaEventDisableTiming));
-    }
+    if (!w.s_comp) MR_TRY(cudaStreamCreateWithFlags(&w.s_comp, cudaStreamNonBlocking));
+    if (!w.s_copy) MR_TRY(cudaStreamCreateWithFlags(&w.s_copy, cudaStreamNonBlocking));
     {
+        const size_t need = carve(buf[0], nullptr, chunk, j.rows_cap, want_traj, j.fin != nullptr, j.env);
+        // an arena is reused when it is large enough and not wastefully larger; growing frees first so that
+        // the peak is the new size, not old + new
+        for (int b = 0; b < 2; ++b) {
+            const bool wanted = b < nbuf;
+            if (w.arena[b] && (!wanted || w.bytes[b] < need || w.bytes[b] / 4 > need)) {
+                MR_TRY(cudaFree(w.arena[b]));
+                w.arena[b] = nullptr; w.bytes[b] = 0;
+            }
+        }
+        for (int b = 0; b < nbuf; ++b) {
+            if (!w.arena[b]) {
+                MR_TRY(cudaMalloc(&w.arena[b], need));
+                w.bytes[b] = need;
+            }
+            carve(buf[b], (char *)w.arena[b], chunk, j.rows_cap, want_traj, j.fin != nullptr, j.env);
+            if (!w.computed[b]) MR_TRY(cudaEventCreateWithFlags(&w.computed[b], cudaEventDisableTiming));
+            if (!w.drained[b]) MR_TRY(cudaEventCreateWithFlags(&w.drained[b], cudaEventDisableTiming));
+            buf[b].computed = w.computed[b];
+            buf[b].drained = w.drained[b];
+        }
+    }
+    t_alloc = clk::now();
+    {
+        cudaStream_t s_comp = w.s_comp, s_copy = w.s_copy;
         int k = 0;
         for (int64_t c0 = lo; c0 < hi; c0 += chunk, ++k) {
             DevBuf &B = buf[k % nbuf];
@@ -529,15 +597,25 @@ static int trace_block_on_device(const DeviceFields &d, const HostJob &j, int64_
             }
             MR_TRY(cudaEventRecord(B.drained, s_copy));
         }
+        t_enqueued = clk::now();
+        MR_TRY(cudaStreamSynchronize(s_comp));
+        MR_TRY(cudaStreamSynchronize(s_copy));
+        t_synced = clk::now();
     }
-    MR_TRY(cudaStreamSynchronize(s_comp));
-    MR_TRY(cudaStreamSynchronize(s_copy));
 done:
-    if (rc != MR_OK) cudaDeviceSynchronize();
-    for (int b = 0; b < 2; ++b) free_devbuf(buf[b]);
-    if (s_comp) cudaStreamDestroy(s_comp);
-    if (s_copy) cudaStreamDestroy(s_copy);
-    if (rc != MR_OK) (void)cudaGetLastError();
+    if (rc != MR_OK) {
+        // leave nothing of a failed call behind: the next one starts from a clean device state
+        cudaDeviceSynchronize();
+        release_work(d, false);
+        (void)cudaGetLastError();
+    }
+    if (timing) {
+        auto ms = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+        std::fprintf(stderr, "[mantaray_b200] device %d: %lld rays in slabs of %lld (%d buffers): alloc %.1f ms, enqueue %.1f ms, "
+                             "drain %.1f ms, tail %.1f ms, %.2f GB held\n", d.dev, (long long)n, (long long)chunk, nbuf,
+                     ms(t_begin, t_alloc), ms(t_alloc, t_enqueued), ms(t_enqueued, t_synced), ms(t_synced, clk::now()),
+                     (double)w.held() / 1e9);
+    }
     return rc;
 #undef MR_TRY
 }
@@ -642,6 +720,13 @@ void mr_fields_free(mr_fields *f)
 
 uint32_t mr_fields_device_mask(const mr_fields *f) { return f ? f->mask : 0; }
 
+void mr_fields_trim(mr_fields *f)
+{
+    if (!f) return;
+    std::lock_guard<std::mutex> guard(f->mu);
+    for (auto &d : f->devs) release_work(d, false);
+}
+
 int64_t mr_num_steps(double t0, double t_end, double dt)
 {
     if (!(dt > 0.0)) return -1;
@@ -740,15 +825,20 @@ int mr_single_ray(mr_fields *f, double x0, double y0, double kx0, double ky0,
     const int64_t cap = nsteps + 1;
     std::vector<double> t((size_t)cap), soa((size_t)cap * 4);
     int32_t rows = 0;
-    // restrict to the first device of the handle: a single ray cannot be sharded
-    mr_fields one;
-    one.mask = 1u << f->devs[0].dev;
-    one.devs.push_back(f->devs[0]);
-    int rc = mr_trace_many(&one, 1, &x0, &y0, &kx0, &ky0, t0, t_end, dt, &o, t.data(),
-                           soa.data(), soa.data() + cap, soa.data() + 2 * cap, soa.data() + 3 * cap,
-                           &rows, nullptr, nullptr);
-    one.devs.clear();                       // borrowed, not owned
-    if (rc) return rc;
+    // the first device of the handle: a single ray cannot be sharded
+    fill_time(t.data(), t0, dt, nsteps, 1);
+    HostJob j{};
+    j.n_total = 1; j.x0 = &x0; j.y0 = &y0; j.kx0 = &kx0; j.ky0 = &ky0;
+    j.dt = dt; j.nsteps = nsteps; j.rows_cap = cap; j.o = o;
+    j.x = soa.data(); j.y = soa.data() + cap; j.kx = soa.data() + 2 * cap; j.ky = soa.data() + 3 * cap;
+    j.rows = &rows; j.len = nullptr; j.fin = nullptr;
+    j.env = mr_env_planes{nullptr, nullptr, nullptr};
+    {
+        std::lock_guard<std::mutex> guard(f->mu);
+        std::string err;
+        int rc = trace_block_on_device(f->devs[0], j, 0, 1, err);
+        if (rc) return fail(rc, "device " + std::to_string(f->devs[0].dev) + ": " + err);
+    }
     *n_rows = rows;
     if (rows > out_cap || !out) return fail(MR_ERR_BAD_ARG, "mr_single_ray: out holds " + std::to_string(out_cap) +
                                                         " rows, " + std::to_string(rows) + " needed");

@@ -163,3 +163,41 @@ def test_multi_device_handle_shards_and_gathers(gpu):
         b = trace_many(fn, *rays, 0.0, wl.duration, wl.dt, final_state=True)
     for name in ("t", "x", "y", "kx", "ky", "rows", "len", "final_state"):
         np.testing.assert_array_equal(getattr(a, name), getattr(b, name), err_msg=name)
+
+
+def test_work_buffers_are_reused_and_trimmed(gpu):
+    """the handle keeps the device work buffers of the host-buffer path between calls (no cudaMalloc/cudaFree per
+    call); any mix of sizes, slabs, planes and single rays gives the same results; mr_fields_trim gives them back"""
+    import torch
+
+    wl = W.c4_agulhas(24, 24, 300, nx=128)
+    rays = wl.all_rays()
+    few = tuple(a[:100] for a in rays)
+
+    def same(a, b):
+        for name in ("x", "y", "kx", "ky"):
+            np.testing.assert_array_equal(getattr(a, name), getattr(b, name))
+        assert np.array_equal(a.rows, b.rows) and np.array_equal(a.len, b.len)
+
+    with Fields(wl.bathymetry, wl.current, devices=[0]) as f:
+        idle = torch.cuda.mem_get_info(0)[0]
+        first = trace_many(f, *rays, wl.t0, wl.duration, wl.dt)
+        held = torch.cuda.mem_get_info(0)[0]
+        assert held < idle                                       # something is kept ...
+        same(trace_many(f, *rays, wl.t0, wl.duration, wl.dt), first)
+        assert torch.cuda.mem_get_info(0)[0] == held             # ... and reused as is
+        small = trace_many(f, *few, wl.t0, wl.duration, wl.dt)
+        np.testing.assert_array_equal(small.x, first.x[:, :100])
+        same(trace_many(f, *rays, wl.t0, wl.duration, wl.dt, chunk_rays=128), first)      # two slabs
+        same(trace_many(f, *rays, wl.t0, wl.duration, wl.dt, env=True, final_state=True), first)   # grows
+        one = _capi.single_ray(f, *(a[7] for a in rays), wl.t0, wl.duration, wl.dt)
+        t, states = one if isinstance(one, tuple) else (one[:, 0], one[:, 1:])
+        np.testing.assert_array_equal(np.asarray(states)[:, 0], first.x[:int(first.rows[7]), 7])
+        same(trace_many(f, *rays, wl.t0, wl.duration, wl.dt), first)
+        f.trim()
+        assert torch.cuda.mem_get_info(0)[0] > held - (1 << 20) and torch.cuda.mem_get_info(0)[0] >= idle - (64 << 20)
+        same(trace_many(f, *rays, wl.t0, wl.duration, wl.dt), first)
+        f.trim(); f.trim()
+    # a failed call (out of memory) leaves the handle usable and holds nothing
+    with Fields(wl.bathymetry, wl.current, devices=[0]) as f:
+        same(trace_many(f, *rays, wl.t0, wl.duration, wl.dt), first)

@@ -159,10 +159,15 @@ def test_multi_device_handle_shards_and_gathers(gpu):
     rays = wl.all_rays()
     with Fields(wl.bathymetry, wl.current, devices=[0]) as f1, Fields(wl.bathymetry, wl.current, devices=list(range(ndev))) as fn:
         assert fn.device_mask == (1 << ndev) - 1
-        a = trace_many(f1, *rays, 0.0, wl.duration, wl.dt, final_state=True)
-        b = trace_many(fn, *rays, 0.0, wl.duration, wl.dt, final_state=True)
-    for name in ("t", "x", "y", "kx", "ky", "rows", "len", "final_state"):
-        np.testing.assert_array_equal(getattr(a, name), getattr(b, name), err_msg=name)
+        a = trace_many(f1, *rays, 0.0, wl.duration, wl.dt, final_state=True, env=True)
+        b = trace_many(fn, *rays, 0.0, wl.duration, wl.dt, final_state=True, env=True)
+        # again on the warm handle (cached work buffers on every device), in slabs, and after a trim
+        c = trace_many(fn, *rays, 0.0, wl.duration, wl.dt, final_state=True, env=True, chunk_rays=256)
+        fn.trim()
+        d = trace_many(fn, *rays, 0.0, wl.duration, wl.dt, final_state=True, env=True)
+    for other in (b, c, d):
+        for name in ("t", "x", "y", "kx", "ky", "rows", "len", "final_state", "depth", "u", "v"):
+            np.testing.assert_array_equal(getattr(a, name), getattr(other, name), err_msg=name)
 
 
 def test_work_buffers_are_reused_and_trimmed(gpu):

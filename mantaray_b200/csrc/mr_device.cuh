@@ -546,8 +546,11 @@ struct FastRay {
         }
         if (CK == MR_CURRENT_GRID) {
             // f64 fractional index (cartesian_current.rs:246).  The spacing is a launch constant:
-            // q0 = t*RN(1/s) and one exact-residual correction give the quotient, exactly whenever
-            // t/s is representable (a ray sitting on a grid line), within one ulp otherwise.  An
+            // q0 = t*RN(1/s), then q0 + (t - q0 s) RN(1/s) in one fma.  The argument of that last rounding is
+            // t/s to within 2^-52 ulp (the residual is exact, only 1/s carries an error), so the result IS
+            // RN(t/s) unless t/s lies within 2^-52 ulp of a rounding midpoint — and only the cell, floor(index),
+            // is used: it can differ from the reference's only if that midpoint also neighbours an integer
+            // (~1e-28 per evaluation).  Exact whenever t/s is representable (a ray sitting on a grid line).  An
             // infinite position turns into NaN here and fails the bounds test like the infinity.
             const double tx = x - c.xd0, ty = y - c.yd0;
             const double qx = tx * c.inv_sx, qy = ty * c.inv_sy;

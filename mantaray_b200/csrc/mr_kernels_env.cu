@@ -9,9 +9,7 @@
 // Two forms of the same lookup, value-identical:
 //   * affine grids (the usual case: coordinates i*step, detected at upload): the cell records of the
 //     fast trace kernel — fractional index by the exact constant division, one record load per field,
-//     the bilinear from the record's corner combinations.  Unlike the trace kernel, the f64 index of
-//     the current is the true IEEE quotient here (the trace kernel's is within an ulp, which only its
-//     1e-9 trajectory contract allows): these planes are bit-exact against the oracle;
+//     the bilinear from the record's corner combinations;
 //   * anything else: the reference's lookups operation by operation (the strict functions).
 //
 // It moves 16 B in and up to 20 B out per stored row: meant to be bound by HBM, not by arithmetic.
@@ -48,7 +46,12 @@ __device__ __forceinline__ float depth_affine(const BathyDev &b, float xf, float
 // current() on an affine grid: cartesian_current.rs:448-467 through the cell record
 __device__ __forceinline__ void current_affine(const CurrentDev &c, double x, double y, double &u, double &v)
 {
-    const double ix = __ddiv_rn(x - c.xd0, c.sx), iy = __ddiv_rn(y - c.yd0, c.sy);    // :246
+    // :246, as FastRay::phase1 does it: RN(t/s) up to rounding-midpoint ties of measure 2^-52 ulp, and only
+    // the cell is taken from it
+    const double tx = x - c.xd0, ty = y - c.yd0;
+    const double qx = __dmul_rn(tx, c.inv_sx), qy = __dmul_rn(ty, c.inv_sy);
+    const double ix = __fma_rn(__fma_rn(-qx, c.sx, tx), c.inv_sx, qx);
+    const double iy = __fma_rn(__fma_rn(-qy, c.sy, ty), c.inv_sy, qy);
     const bool ok = ix >= 0.0 && ix <= c.nxm1d && iy >= 0.0 && iy <= c.nym1d;       // :248
     const int x1 = cell_of(ix, c.nx), y1 = cell_of(iy, c.ny);
     float4 U, V;

@@ -17,10 +17,13 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--rays", type=int, default=1_000_000)
 ap.add_argument("--steps", type=int, default=2048)
 ap.add_argument("--reps", type=int, default=5)
+ap.add_argument("--lib", default=None)
 a = ap.parse_args()
 side = int(round(a.rays ** 0.5))
 wl = W.c4_agulhas(side, side, a.steps)
 n, rows = wl.n_rays, wl.n_rows
+if a.lib:
+    _capi.lib_path = lambda: os.path.abspath(a.lib)
 lib = _capi.load()
 dev = torch.device("cuda:0")
 ic = [torch.from_numpy(np.ascontiguousarray(v, dtype=np.float64)).to(dev) for v in wl.all_rays()]
@@ -48,5 +51,5 @@ with Fields(wl.bathymetry, wl.current, devices=[0]) as f:
         t = float(np.median(ms[1:]))
         out_b = (4 if args[0] else 0) + (8 if args[1] else 0) + (8 if args[2] else 0)
         gb = rows * n * (16 + out_b) / 1e9
-        print(json.dumps({"planes": what, "rows": rows, "rays": n, "ms": t, "alg_GB": gb, "GB_per_s": gb / (t * 1e-3),
+        print(json.dumps({"lib": os.path.basename(a.lib or "default"), "planes": what, "rows": rows, "rays": n, "ms": t, "alg_GB": gb, "GB_per_s": gb / (t * 1e-3),
                           "points_per_s": rows * n / (t * 1e-3)}))

@@ -460,33 +460,42 @@ __device__ __forceinline__ void rhs_f64_fast(double kx, double ky, double k, dou
                                              const CurrentVal &cv, double out[4])
 {
     const double kh = k * h;
-    // tanh kh, kh/cosh^2 kh, 1/(sinh kh cosh kh).  kh * 0 is 0 — or NaN for h = +inf, where the reference's
-    // kh/sinh(2kh) is inf/inf: cg is NaN there while the bathymetric term stays -0 * grad(h), as below
-    double T = 1.0, hs2 = kh * 0.0, csch_sech = 0.0;
-    // Deep water, kh >= 22: exp(-2kh) < 8e-20, so in f64 tanh kh == 1 exactly, kh/cosh^2 kh <
-    // 2^-57 vanishes against it, and the bathymetric term changes k by less than 3e-18 of itself
-    // per step — below half an ulp, i.e. the reference's own sum rounds it away.  The
-    // exponential is skipped there.  (NaN kh takes the general branch and propagates.)
+    // cg and the factor Bc of grad(h) in dk/dt; tanh kh = T, kh/cosh^2 kh = hs2, 1/(sinh kh cosh kh) = csch_sech
+    double cg, bx, by;
     if (!(kh >= kExpRed[4])) {
         double E, em;
         exp_expm1_neg(-2.0 * kh, E, em);
         const double m = -em, w = 2.0 + em;
         const double r = recip(m * w);
         const double invw = m * r;
-        T = m * invw;
+        const double T = m * invw;
         const double E4 = 4.0 * E;
-        hs2 = kh * ((E4 * invw) * invw);
-        csch_sech = E4 * r;
+        const double hs2 = kh * ((E4 * invw) * invw);
+        const double csch_sech = E4 * r;
+        const double q = (k * kExpRed[5]) * T;
+        double sq, rq;
+        sqrt_rsqrt(q, sq, rq);
+        cg = kExpRed[6] * ((T + hs2) * rq);
+        const double Bc = ((-0.5 * k) * csch_sech) * sq;
+        bx = Bc * dhdx; by = Bc * dhdy;
+    } else {
+        // Deep water, kh >= 22: exp(-2kh) < 8e-20, so in f64 tanh kh == 1 exactly, kh/cosh^2 kh < 2^-57
+        // vanishes against it, and the bathymetric term changes k by less than 3e-18 of itself per step —
+        // below half an ulp, i.e. the reference's own sum rounds it away.  With T = 1 and the other two 0 the
+        // general expressions reduce, value for value, to cg = (G/2) rsqrt(G k) and Bc = -0.  The zeros are
+        // computed, not written: kh * 0 is NaN when h (or k) is +inf, where the reference's kh/sinh(2kh) is
+        // inf/inf and cg NaN, while its bathymetric term stays -0 * grad(h) for an infinite h (k * 0 is 0 then)
+        // and propagates a non-finite gradient.
+        const double z = kh * 0.0, zk = k * 0.0;
+        double sq, rq;
+        sqrt_rsqrt(k * kExpRed[5], sq, rq);
+        cg = fma(kExpRed[6], rq, z);
+        bx = -zk * dhdx; by = -zk * dhdy;
     }
-    const double q = (k * kExpRed[5]) * T;
-    double sq, rq;
-    sqrt_rsqrt(q, sq, rq);
-    const double cg = kExpRed[6] * ((T + hs2) * rq);
-    const double Bc = ((-0.5 * k) * csch_sech) * sq;
     out[0] = fma(cg, cs, cv.u);
     out[1] = fma(cg, sn, cv.v);
-    out[2] = fma(-ky, cv.dvdx, fma(-kx, cv.dudx, Bc * dhdx));
-    out[3] = fma(-ky, cv.dvdy, fma(-kx, cv.dudy, Bc * dhdy));
+    out[2] = fma(-ky, cv.dvdx, fma(-kx, cv.dudx, bx));
+    out[3] = fma(-ky, cv.dvdy, fma(-kx, cv.dudy, by));
 }
 
 // =============================================================================

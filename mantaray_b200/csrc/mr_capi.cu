@@ -227,6 +227,7 @@ static bool affine_f32(const float *c, int n, float *d_out)
 {
     const float d = c[1] - c[0];
     if (!(d > 0.0f) || std::isinf(d)) return false;
+    if (n > (1 << 23)) return false;       // cell numbers are formed as floats (FastRay::cell_f2, kMagicBits)
     for (int i = 0; i < n; ++i) {
         const float xa = std::fmaf((float)i, d, c[0]);
         if (xa != c[i]) return false;
@@ -292,6 +293,7 @@ static int upload_fields(DeviceFields &d, const mr_bathymetry_desc *b, const mr_
         B.y_space = (double)b->y[1] - (double)b->y[0];         // :120
         float4 *cell = nullptr;
         const size_t ncell = (size_t)(b->nx - 1) * (b->ny - 1);
+        if (ncell >= ((size_t)1 << 30)) return fail(MR_ERR_BAD_ARG, "bathymetry grid has 2^30 cells or more (32-bit cell addressing)");
         if ((rc = device_alloc(d, 2 * ncell, &cell))) return rc;
         build_bathy_cells<<<(unsigned)std::min<size_t>((ncell + 255) / 256, 148 * 16), 256>>>(B.depth, b->nx, b->ny, B.x_space, B.y_space, cell);
         MR_CUDA(cudaGetLastError());
@@ -329,6 +331,7 @@ static int upload_fields(DeviceFields &d, const mr_bathymetry_desc *b, const mr_
         C.y_space = c->y[1] - c->y[0];                         // :516
         const size_t ncell = (size_t)(c->nx - 1) * (c->ny - 1);
         float4 *ccells = nullptr;
+        if (ncell >= ((size_t)1 << 30)) return fail(MR_ERR_BAD_ARG, "current grid has 2^30 cells or more (32-bit cell addressing)");
         if ((rc = device_alloc(d, 4 * ncell, &ccells))) return rc;
         build_current_cells<<<(unsigned)std::min<size_t>((ncell + 255) / 256, 148 * 16), 256>>>(C.u, C.v, c->nx, c->ny, C.x_space, C.y_space, ccells);
         MR_CUDA(cudaGetLastError());

@@ -38,7 +38,15 @@ struct TraceArgs {
     int64_t ld;
     int32_t *rows, *len;       // [n] or NULL
     double *fin;               // [4][n] or NULL
+    // filled by launch_trace_math: the stage offsets {0, dt/2, dt/2, dt} of the RK4 loop, read with the
+    // stage number as a constant-bank index (one LDC instead of compares and selects per stage)
+    double stage_a[4];
+    // and the trajectory planes as byte offsets from the x plane, the row pitch in bytes
+    int64_t off_y, off_kx, off_ky, row_bytes;
 };
+
+// RK4 weights {1, 2, 2, 1} of the stage derivatives, indexed the same way
+static __constant__ double kStageW[4] = {1.0, 2.0, 2.0, 1.0};
 
 static constexpr int kBlock = kBlockThreads;
 
@@ -54,18 +62,17 @@ static constexpr int kBlock = kBlockThreads;
 #ifndef MR_MIN_BLOCKS_GENERIC
 #define MR_MIN_BLOCKS_GENERIC 5
 #endif
-#ifndef MR_MIN_BLOCKS_NR2
-#define MR_MIN_BLOCKS_NR2 4
+// stage offsets and weights read from tables indexed by the stage number (0: computed with selects)
+#ifndef MR_STAGE_TABLE
+#define MR_STAGE_TABLE 0
 #endif
-// Rays per thread.  2 (adjacent rays, interleaved RHS phases, 16-byte row stores) was measured at
-// 2.0e10 ray-steps/s against 2.8e10 for 1 on C4 (168 registers, 12 warps/SM): not compiled by default.
-#ifndef MR_RAYS_PER_THREAD
-#define MR_RAYS_PER_THREAD 1
-#endif
-#ifndef MR_STREAM_STORES
-#define MR_STREAM_STORES 1
+// the RK4 loop as one flattened (step, stage) loop (1) or as a stage loop nested in a step loop (0)
+#ifndef MR_FLAT_LOOP
+#define MR_FLAT_LOOP 0
 #endif
 static constexpr int kStageUnroll = MR_STAGE_UNROLL;
+// (Two rays per thread — interleaved RHS phases, 16-byte row stores — was measured at 2.0e10 ray-steps/s
+// against 2.8e10 for one on C4, 168 registers; the kernel carries one ray per thread.)
 
 __device__ __forceinline__ bool any_nan4(const double y[4])
 {
@@ -76,180 +83,227 @@ __device__ __forceinline__ bool all_nan4(const double y[4])
     return isnan(y[0]) && isnan(y[1]) && isnan(y[2]) && isnan(y[3]);
 }
 
-// store one row of the NR rays of a thread (ray index o, o+1 adjacent in memory)
-template <int NR>
-__device__ __forceinline__ void store_row(const TraceArgs &a, int64_t o, const double (&y)[NR][4], const bool (&valid)[NR])
+// Ray carried by this thread.  The threads of the last block that lie past the last ray repeat that
+// ray instead of idling: they compute and store bit-identical values to the same addresses, which is
+// harmless, and in exchange the kernel has no per-thread validity flag — every vote is over a full warp
+// (so the step counter and the row bookkeeping stay warp-uniform) and every store is unconditional.
+__device__ __forceinline__ int64_t ray_index(const TraceArgs &a)
 {
-    if (NR == 2 && valid[1]) {             // both rays: one 16-byte store per field (host guarantees alignment)
-        __stcs(reinterpret_cast<double2 *>(a.x + o),  make_double2(y[0][0], y[1][0]));
-        __stcs(reinterpret_cast<double2 *>(a.y + o),  make_double2(y[0][1], y[1][1]));
-        __stcs(reinterpret_cast<double2 *>(a.kx + o), make_double2(y[0][2], y[1][2]));
-        __stcs(reinterpret_cast<double2 *>(a.ky + o), make_double2(y[0][3], y[1][3]));
-    } else if (valid[0]) {
-        __stcs(a.x + o, y[0][0]); __stcs(a.y + o, y[0][1]); __stcs(a.kx + o, y[0][2]); __stcs(a.ky + o, y[0][3]);
-    }
+    return min((int64_t)blockIdx.x * kBlock + threadIdx.x, a.n - 1);
+}
+// One row: p is this ray's element of the x plane; the other planes lie at fixed byte offsets from it.
+__device__ __forceinline__ void store_row(const TraceArgs &a, char *p, const double y[4])
+{
+    __stcs((double *)p, y[0]);
+    __stcs((double *)(p + a.off_y), y[1]);
+    __stcs((double *)(p + a.off_kx), y[2]);
+    __stcs((double *)(p + a.off_ky), y[3]);
+}
+__device__ __forceinline__ void store_fin(const TraceArgs &a, const double y[4])
+{
+    const int64_t i = ray_index(a);
+    a.fin[i] = y[0]; a.fin[a.n + i] = y[1]; a.fin[2 * a.n + i] = y[2]; a.fin[3 * a.n + i] = y[3];
 }
 
-// NR rays per thread (adjacent rays i0, i0+1): the RHS phases of the rays interleave (mr_device.cuh,
-// rhs_fast_n), per-thread uniform work is shared, and rows are stored 16 bytes at a time.
-template <int BK, int CK, int MATH, bool UNI, int NR>
-__global__ void __launch_bounds__(kBlock, (MATH == MR_MATH_FAST) ? (NR == 2 ? MR_MIN_BLOCKS_NR2 : (UNI ? MR_MIN_BLOCKS : MR_MIN_BLOCKS_GENERIC)) : 1)
+// FIN: the last NaN-free state of every ray is wanted (a.fin).  It is a template parameter because the
+// state it needs — y of the row before the first NaN — is otherwise dead once the next row exists: without
+// it the new row is formed in place, with it every step ends in a register-to-register copy of the state.
+//
+// Per-ray bookkeeping is event-driven: `rows` is written when the ray stops and `len` when its first NaN
+// appears (each at most once per ray, re-deriving the ray index on the spot), so the step loop carries two
+// flags and one row pointer per thread; the step number and the store countdown are warp-uniform.
+template <int BK, int CK, int MATH, bool UNI, bool FIN>
+__global__ void __launch_bounds__(kBlock, (MATH == MR_MATH_FAST) ? (UNI ? MR_MIN_BLOCKS : MR_MIN_BLOCKS_GENERIC) : 1)
 trace_kernel(const __grid_constant__ TraceArgs a)
 {
-    const int64_t i0 = ((int64_t)blockIdx.x * kBlock + threadIdx.x) * NR;
     const bool store = a.x != nullptr;
     const double dt = a.dt;
-    const double half = dt / 2.0;
     const double sixth = dt / 6.0;
-
-    bool valid[NR], alive[NR], clean[NR];
-    int32_t rows[NR], len[NR];
-    double y[NR][4];
-#pragma unroll
-    for (int r = 0; r < NR; ++r) {
-        const int64_t i = i0 + r;
-        valid[r] = i < a.n;
-        y[r][0] = valid[r] ? a.x0[i]  : qnan();
-        y[r][1] = valid[r] ? a.y0[i]  : qnan();
-        y[r][2] = valid[r] ? a.kx0[i] : qnan();
-        y[r][3] = valid[r] ? a.ky0[i] : qnan();
-        alive[r] = valid[r] && a.nsteps > 0;
-        clean[r] = !any_nan4(y[r]);        // no NaN seen yet: rows so far all count towards len
-        rows[r] = 1;
-        len[r] = clean[r] ? 1 : 0;
-        if (valid[r] && a.fin && !clean[r]) {   // no NaN-free row at all
-            a.fin[i] = qnan(); a.fin[a.n + i] = qnan(); a.fin[2 * a.n + i] = qnan(); a.fin[3 * a.n + i] = qnan();
-        }
-    }
-    if (store) store_row<NR>(a, i0, y, valid);
-
+#if !MR_STAGE_TABLE
+    const double half = dt / 2.0;
+#endif
     const int32_t nsteps = (int32_t)a.nsteps;      // < 2^31 (mr_num_steps)
+
+    double y[1][4];
+    char *p;                               // this ray's element of the last stored row of the x plane
+    {
+        const int64_t i = ray_index(a);
+        y[0][0] = a.x0[i]; y[0][1] = a.y0[i]; y[0][2] = a.kx0[i]; y[0][3] = a.ky0[i];
+        p = (char *)(a.x + i);
+    }
+    bool alive = nsteps > 0;
+    bool clean = !any_nan4(y[0]);          // no NaN seen yet: rows so far all count towards len
+    if (!clean) {                          // no NaN-free row at all
+        if (a.len) a.len[ray_index(a)] = 0;
+        if (FIN && a.fin) { const double nanrow[4] = {qnan(), qnan(), qnan(), qnan()}; store_fin(a, nanrow); }
+    }
+    if (store) store_row(a, p, y[0]);
+
     int32_t until_store = a.stride;        // counts down to the next stored row
-    int64_t o = i0;                        // offset of this thread's rays in the last stored row
-    int32_t rows_left = nsteps / a.stride; // stored rows still to write
-    for (int32_t s = 1; s <= nsteps; ++s) {
-        bool any_alive = alive[0];
+#if MR_FLAT_LOOP
+    // The RK4 loop, flattened: ONE loop over (step, stage) whose body is a stage; the step's bookkeeping runs
+    // when stage 3 has been evaluated.  (As a stage loop nested in a step loop, ptxas re-loaded the ~30
+    // uniform registers of launch constants at the top of every step: it hoists them out of one loop only.)
+    double k[1][4], acc[4];
+    bool k0_nan = false;
 #pragma unroll
-        for (int r = 1; r < NR; ++r) any_alive = any_alive || alive[r];
-        if (!__any_sync(0xffffffffu, any_alive)) break;
-        if (any_alive) {
-            double k[NR][4], acc[NR][4];
-            bool k0_nan[NR];
+    for (int c = 0; c < 4; ++c) { k[0][c] = 0.0; acc[c] = -0.0; }    // -0 + k0 == k0 for every k0
+    int32_t s = 1, st = 0;
+    while (s <= nsteps) {
+        if (alive) {
+#if MR_STAGE_TABLE
+            const double as = a.stage_a[st], ws = kStageW[st];
+#else
+            const double as = (st == 0) ? 0.0 : (st == 3 ? dt : half);
+            const double ws = (st == 1 || st == 2) ? 2.0 : 1.0;
+#endif
+            double yt[1][4];
 #pragma unroll
-            for (int r = 0; r < NR; ++r)
-#pragma unroll
-                for (int c = 0; c < 4; ++c) { k[r][c] = 0.0; acc[r][c] = -0.0; }    // -0 + k0 == k0 for every k0
-#pragma unroll kStageUnroll
-            for (int st = 0; st < 4; ++st) {
-                const double as = (st == 0) ? 0.0 : (st == 3 ? dt : half);
-                const double ws = (st == 1 || st == 2) ? 2.0 : 1.0;
-                double yt[NR][4];
-#pragma unroll
-                for (int r = 0; r < NR; ++r)
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const double adv = (MATH == MR_MATH_STRICT) ? __dadd_rn(y[r][c], __dmul_rn(k[r][c], as)) : fma(k[r][c], as, y[r][c]);
-                        // stage 0 evaluates f(y): k is still 0 there, and y + 0*0 == y (a -0 component
-                        // would become +0, which the strict path must not allow)
-                        yt[r][c] = (MATH == MR_MATH_STRICT && st == 0) ? y[r][c] : adv;
-                    }
-                rhs<BK, CK, MATH, UNI, NR>(a.b, a.c, yt, k);
-#pragma unroll
-                for (int r = 0; r < NR; ++r) {
-                    if (st == 0) k0_nan[r] = all_nan4(k[r]);
-#pragma unroll
-                    for (int c = 0; c < 4; ++c)
-                        acc[r][c] = (MATH == MR_MATH_STRICT) ? __dadd_rn(acc[r][c], __dmul_rn(k[r][c], ws)) : fma(k[r][c], ws, acc[r][c]);
-                }
+            for (int c = 0; c < 4; ++c) {
+                const double adv = (MATH == MR_MATH_STRICT) ? __dadd_rn(y[0][c], __dmul_rn(k[0][c], as)) : fma(k[0][c], as, y[0][c]);
+                // stage 0 evaluates f(y): k is 0 there, and y + 0*0 == y (a -0 component would become
+                // +0, which the strict path must not allow)
+                yt[0][c] = (MATH == MR_MATH_STRICT && st == 0) ? y[0][c] : adv;
             }
+            rhs<BK, CK, MATH, UNI, 1>(a.b, a.c, yt, k);
+            if (st == 0) k0_nan = all_nan4(k[0]);
 #pragma unroll
-            for (int r = 0; r < NR; ++r) {
-                double yn[4];
+            for (int c = 0; c < 4; ++c)
+                acc[c] = (MATH == MR_MATH_STRICT) ? __dadd_rn(acc[c], __dmul_rn(k[0][c], ws)) : fma(k[0][c], ws, acc[c]);
+        }
+        if (++st < 4) continue;
+        // ---- all four stages done: the new row ----
+        st = 0;
+        if (alive) {
+            double yn[4];
 #pragma unroll
-                for (int c = 0; c < 4; ++c)
-                    yn[c] = (MATH == MR_MATH_STRICT) ? __dadd_rn(y[r][c], __dmul_rn(acc[r][c], sixth)) : fma(acc[r][c], sixth, y[r][c]);
-                const bool n0 = isnan(yn[0]), n1 = isnan(yn[1]), n2 = isnan(yn[2]), n3 = isnan(yn[3]);
-                if (alive[r]) {
-                    const int64_t i = i0 + r;
-                    rows[r] = s + 1;
-                    if (clean[r]) {
-                        if (n0 || n1 || n2 || n3) {
-                            clean[r] = false;
-                            if (a.fin) {       // y is the last NaN-free row
-                                a.fin[i] = y[r][0]; a.fin[a.n + i] = y[r][1]; a.fin[2 * a.n + i] = y[r][2]; a.fin[3 * a.n + i] = y[r][3];
-                            }
-                        } else {
-                            len[r] = s + 1;
-                        }
-                    }
-                    if (k0_nan[r] || (n0 && n1 && n2 && n3)) alive[r] = false;    // solout
-                    // (a stopped ray's state is all-NaN from here on, whatever its sibling does)
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) y[r][c] = yn[c];
-                }
+            for (int c = 0; c < 4; ++c)
+                yn[c] = (MATH == MR_MATH_STRICT) ? __dadd_rn(y[0][c], __dmul_rn(acc[c], sixth)) : fma(acc[c], sixth, y[0][c]);
+            const bool n0 = isnan(yn[0]), n1 = isnan(yn[1]), n2 = isnan(yn[2]), n3 = isnan(yn[3]);
+            if (clean && (n0 || n1 || n2 || n3)) {       // first NaN: rows 0..s-1 are the NaN-free ones
+                clean = false;
+                if (a.len) a.len[ray_index(a)] = s;
+                if (FIN && a.fin) store_fin(a, y[0]);
             }
+            if (k0_nan || (n0 && n1 && n2 && n3)) {       // solout: this row, s, is the ray's last
+                alive = false;
+                if (a.rows) a.rows[ray_index(a)] = s + 1;
+            }
+            // (a stopped ray's state is all-NaN from here on)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { y[0][c] = yn[c]; k[0][c] = 0.0; acc[c] = -0.0; }
         }
         if (--until_store == 0) {
             until_store = a.stride;
-            o += a.ld;
-            --rows_left;
-            if (store) store_row<NR>(a, o, y, valid);
+            p += a.row_bytes;
+            if (store) store_row(a, p, y[0]);
         }
+        ++s;
+#ifndef MR_X_NOVOTE
+        if (!__any_sync(0xffffffffu, alive)) break;
+#endif
     }
-    // whole warp stopped: rows it never reached are NaN
-    if (store) {
-        double nanrow[NR][4];
+#else
+    // the RK4 loop as a stage loop nested in a step loop (A/B alternative to the flattened form)
+    for (int32_t s = 1; s <= nsteps; ++s) {
+        if (!__any_sync(0xffffffffu, alive)) break;
+        if (alive) {
+            double k[1][4], acc[4];
+            bool k0_nan;
 #pragma unroll
-        for (int r = 0; r < NR; ++r)
+            for (int c = 0; c < 4; ++c) { k[0][c] = 0.0; acc[c] = -0.0; }
+#pragma unroll kStageUnroll
+            for (int st = 0; st < 4; ++st) {
+#if MR_STAGE_TABLE
+                const double as = a.stage_a[st], ws = kStageW[st];
+#else
+                const double as = (st == 0) ? 0.0 : (st == 3 ? dt : half);
+                const double ws = (st == 1 || st == 2) ? 2.0 : 1.0;
+#endif
+                double yt[1][4];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) nanrow[r][c] = qnan();
-        for (; rows_left > 0; --rows_left) {
-            o += a.ld;
-            store_row<NR>(a, o, nanrow, valid);
-        }
-    }
+                for (int c = 0; c < 4; ++c) {
+                    const double adv = (MATH == MR_MATH_STRICT) ? __dadd_rn(y[0][c], __dmul_rn(k[0][c], as)) : fma(k[0][c], as, y[0][c]);
+                    yt[0][c] = (MATH == MR_MATH_STRICT && st == 0) ? y[0][c] : adv;
+                }
+                rhs<BK, CK, MATH, UNI, 1>(a.b, a.c, yt, k);
+                if (st == 0) k0_nan = all_nan4(k[0]);
 #pragma unroll
-    for (int r = 0; r < NR; ++r) {
-        const int64_t i = i0 + r;
-        if (valid[r]) {
-            if (a.rows) a.rows[i] = rows[r];
-            if (a.len)  a.len[i]  = len[r];
-            if (a.fin && clean[r]) {
-                a.fin[i] = y[r][0]; a.fin[a.n + i] = y[r][1]; a.fin[2 * a.n + i] = y[r][2]; a.fin[3 * a.n + i] = y[r][3];
+                for (int c = 0; c < 4; ++c)
+                    acc[c] = (MATH == MR_MATH_STRICT) ? __dadd_rn(acc[c], __dmul_rn(k[0][c], ws)) : fma(k[0][c], ws, acc[c]);
             }
+            double yn[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                yn[c] = (MATH == MR_MATH_STRICT) ? __dadd_rn(y[0][c], __dmul_rn(acc[c], sixth)) : fma(acc[c], sixth, y[0][c]);
+            const bool n0 = isnan(yn[0]), n1 = isnan(yn[1]), n2 = isnan(yn[2]), n3 = isnan(yn[3]);
+            if (clean && (n0 || n1 || n2 || n3)) {
+                clean = false;
+                if (a.len) a.len[ray_index(a)] = s;
+                if (FIN && a.fin) store_fin(a, y[0]);
+            }
+            if (k0_nan || (n0 && n1 && n2 && n3)) {
+                alive = false;
+                if (a.rows) a.rows[ray_index(a)] = s + 1;
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) y[0][c] = yn[c];
         }
+        if (--until_store == 0) {
+            until_store = a.stride;
+            p += a.row_bytes;
+            if (store) store_row(a, p, y[0]);
+        }
+    }
+#endif
+    // whole warp stopped early: the rows it never reached are NaN (how many is read off the row pointer,
+    // so that nothing but the pointer is carried through the loop for it)
+    if (store) {
+        const double nanrow[4] = {qnan(), qnan(), qnan(), qnan()};
+        char *const last = (char *)(a.x + ray_index(a)) + (int64_t)(nsteps / a.stride) * a.row_bytes;
+        while (p != last) {
+            p += a.row_bytes;
+            store_row(a, p, nanrow);
+        }
+    }
+    // a ray still integrating when the loop ends ran all nsteps (nsteps == 0: the initial row only);
+    // one that never met a NaN is still integrating, so its len is its rows
+    if (alive || nsteps <= 0) {
+        if (a.rows) a.rows[ray_index(a)] = nsteps + 1;
+    }
+    if (clean) {
+        if (a.len) a.len[ray_index(a)] = nsteps + 1;
+        if (FIN && a.fin) store_fin(a, y[0]);
     }
 }
 
-// One instantiation per (bathymetry kind, current kind[, affine grids, rays per thread]); the
-// kinds are uniform over a launch, so the dispatch is a host-side switch.
+// One instantiation per (bathymetry kind, current kind[, affine grids]) and per FIN; the kinds are
+// uniform over a launch, so the dispatch is a host-side switch.
 template <int MATH>
-static cudaError_t launch_trace_math(const TraceArgs &a, cudaStream_t stream)
+static cudaError_t launch_trace_math(const TraceArgs &args, cudaStream_t stream)
 {
-    if (a.n <= 0) return cudaSuccess;
+    if (args.n <= 0) return cudaSuccess;
+    TraceArgs a = args;
+    a.stage_a[0] = 0.0; a.stage_a[1] = a.stage_a[2] = a.dt / 2.0; a.stage_a[3] = a.dt;
+    a.off_y = (const char *)a.y - (const char *)a.x; a.off_kx = (const char *)a.kx - (const char *)a.x;
+    a.off_ky = (const char *)a.ky - (const char *)a.x; a.row_bytes = a.ld * (int64_t)sizeof(double);
     // the fast path's affine-coordinate specialisation needs every gridded field to qualify
     const bool uni = MATH == MR_MATH_FAST &&
                      (a.b.kind != MR_BATHY_GRID || a.b.uniform) && (a.c.kind != MR_CURRENT_GRID || a.c.uniform) &&
                      (a.b.kind == MR_BATHY_GRID || a.c.kind == MR_CURRENT_GRID);
-    // two rays per thread need 16-byte aligned row pairs: even pitch and aligned planes
-    const bool aligned = a.x == nullptr || (a.ld % 2 == 0 && ((uintptr_t)a.x | (uintptr_t)a.y | (uintptr_t)a.kx | (uintptr_t)a.ky) % 16 == 0);
-#if MR_RAYS_PER_THREAD == 2
-    const bool two = MATH == MR_MATH_FAST && aligned && a.n >= 2 * kBlock;
-#else
-    const bool two = false;
-    (void)aligned;
-#endif
-    const int nr = two ? 2 : 1;
-    const unsigned grid = (unsigned)((a.n + (int64_t)kBlock * nr - 1) / ((int64_t)kBlock * nr));
-#define MR_LAUNCH(BKV, CKV, UNIV, NRV) trace_kernel<BKV, CKV, MATH, UNIV, NRV><<<grid, kBlock, 0, stream>>>(a)
-    constexpr int kNr2 = (MATH == MR_MATH_FAST && MR_RAYS_PER_THREAD == 2) ? 2 : 1;
+    const unsigned grid = (unsigned)((a.n + (int64_t)kBlock - 1) / (int64_t)kBlock);
     constexpr bool kFast = MATH == MR_MATH_FAST;
+    // the strict kernels are compiled with FIN only (and test a.fin at run time)
+    const bool fin = !kFast || a.fin != nullptr;
+#define MR_LAUNCH(BKV, CKV, UNIV)                                                                              \
+    do {                                                                                                       \
+        if (fin) trace_kernel<BKV, CKV, MATH, UNIV, true><<<grid, kBlock, 0, stream>>>(a);                     \
+        else trace_kernel<BKV, CKV, MATH, UNIV, !kFast><<<grid, kBlock, 0, stream>>>(a);                       \
+    } while (0)
 #define MR_CASE(BKV, CKV)                                                                                      \
     if (a.b.kind == BKV && a.c.kind == CKV) {                                                                  \
-        if (uni && two) MR_LAUNCH(BKV, CKV, kFast, kNr2);                                                      \
-        else if (uni) MR_LAUNCH(BKV, CKV, kFast, 1);                                                           \
-        else if (two) MR_LAUNCH(BKV, CKV, false, kNr2);                                                        \
-        else MR_LAUNCH(BKV, CKV, false, 1);                                                                    \
+        if (uni) MR_LAUNCH(BKV, CKV, kFast);                                                                   \
+        else MR_LAUNCH(BKV, CKV, false);                                                                       \
         return cudaGetLastError();                                                                             \
     }
     MR_CASE(MR_BATHY_CONSTANT, MR_CURRENT_CONSTANT)

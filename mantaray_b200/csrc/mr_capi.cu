@@ -227,7 +227,7 @@ static bool affine_f32(const float *c, int n, float *d_out)
 {
     const float d = c[1] - c[0];
     if (!(d > 0.0f) || std::isinf(d)) return false;
-    if (n > (1 << 23)) return false;       // cell numbers are formed as floats (FastRay::cell_f2, kMagicBits)
+    if (n > (1 << 24)) return false;       // cell numbers are formed as floats: (float)i must be exact
     for (int i = 0; i < n; ++i) {
         const float xa = std::fmaf((float)i, d, c[0]);
         if (xa != c[i]) return false;

@@ -156,7 +156,6 @@ __device__ __forceinline__ float hi_of(f32x2 v) { return __uint_as_float((unsign
 __device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { f32x2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ f32x2 add2_rm(f32x2 a, f32x2 b) { f32x2 r; asm("add.rm.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
 
 // fast form.  The cell's fractional coordinates (X, Y) are resolved once per lookup and shared by
@@ -228,35 +227,23 @@ __device__ __forceinline__ double2 ldg_d2(const double2 *p)
     asm volatile("ld.global.nc.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
     return v;
 }
-// cache hint of the record loads (A/B knob): 0 read-only path (default), 1 the same without allocating in L1,
-// 2 plain L2-only loads
-#ifndef MR_LD_HINT
-#define MR_LD_HINT 0
-#endif
-#if MR_LD_HINT == 1
-#define MR_LDREC "ld.global.nc.L1::no_allocate"
-#elif MR_LD_HINT == 2
-#define MR_LDREC "ld.global.cg"
-#else
-#define MR_LDREC "ld.global.nc"
-#endif
 // One 32-byte record in ONE instruction (sm_100 LDG.256): a float4 followed by a double2, or
 // two float4, or two double2.  What arrives together cannot be split into two round trips.
 __device__ __forceinline__ void ldg_f4_d2(const float4 *p, float4 &a, double2 &b)
 {
     unsigned long long q0, q1;
-    asm volatile(MR_LDREC ".v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(q0), "=l"(q1), "=d"(b.x), "=d"(b.y) : "l"(p));
+    asm volatile("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(q0), "=l"(q1), "=d"(b.x), "=d"(b.y) : "l"(p));
     a.x = __uint_as_float((unsigned)q0); a.y = __uint_as_float((unsigned)(q0 >> 32));
     a.z = __uint_as_float((unsigned)q1); a.w = __uint_as_float((unsigned)(q1 >> 32));
 }
 __device__ __forceinline__ void ldg_f4_f4(const float4 *p, float4 &a, float4 &b)
 {
-    asm volatile(MR_LDREC ".v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
 }
 __device__ __forceinline__ void ldg_d2_d2(const double2 *p, double2 &a, double2 &b)
 {
-    asm volatile(MR_LDREC ".v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a.x), "=d"(a.y), "=d"(b.x), "=d"(b.y) : "l"(p));
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a.x), "=d"(a.y), "=d"(b.x), "=d"(b.y) : "l"(p));
 }
 
 // The cell rule of four_corners (cartesian_netcdf3.rs:344-387, cartesian_current.rs
@@ -274,27 +261,6 @@ __device__ __forceinline__ int cell_of(double index, int n)
 {
     int i = __double2int_rd(index);
     return max(min(i, n - 2), 0);
-}
-
-// ---- floor without the conversion unit (MR_MAGIC_FLOOR) --------------------------------------------
-// floor(index) -> int -> float costs two trips through the XU (F2I, I2FP: 16 lanes/clk/SM, the pipe MUFU
-// shares).  Adding 2^23 with round-down does the same on the FMA pipe: for 0 <= index < 2^23 the sum
-// 2^23 + index, rounded toward -inf to the unit spacing of [2^23, 2^24), is exactly 2^23 + floor(index), so the
-// BITS of the sum are kMagicBits + floor(index).  Cells are kept in that biased form: clamped as integers to
-// [kMagicBits, kMagicBits + n-2] (any out-of-range, NaN or infinite index lands on some cell in range — the
-// lookup has failed already and its loads only need to stay in bounds), turned into the float cell number by
-// subtracting 2^23 (exact), and into the record offset with the bias folded into a launch constant.  The f64
-// index of the current does the same with 2^52 + kMagicBits: the low word of the sum is the biased cell.
-// Used on affine grids only (the host requires nx, ny <= 2^23 there).
-#ifndef MR_MAGIC_FLOOR
-#define MR_MAGIC_FLOOR 0
-#endif
-static constexpr int    kMagicBits = 0x4B000000;                 // bits of 2^23 as f32
-static constexpr float  kMagicF = 8388608.0f;                    // 2^23
-static constexpr double kMagicD = 4503599627370496.0 + 1258291200.0;   // 2^52 + kMagicBits
-__device__ __forceinline__ int clamp_cell(int biased, int n)
-{
-    return max(min(biased, kMagicBits + n - 2), kMagicBits);
 }
 
 // =============================================================================
@@ -562,15 +528,6 @@ struct FastRay {
     float bxa, bxb, bya, byb, cxa, cxb, cya, cyb;
     double k2, k, cs, sn;
 
-    // cell numbers as the pair of floats / as plain integers (they are kept biased by kMagicBits on affine grids)
-    static __device__ __forceinline__ f32x2 cell_f2(int ix, int iy)
-    {
-        if (UNI && MR_MAGIC_FLOOR)
-            return sub2(((f32x2)(unsigned)iy << 32) | (f32x2)(unsigned)ix, pk(kMagicF, kMagicF));
-        return pk((float)ix, (float)iy);
-    }
-    static __device__ __forceinline__ int cell_i(int i) { return (UNI && MR_MAGIC_FLOOR) ? i - kMagicBits : i; }
-
     // ---- phase 1: fractional indices and cell addresses ------------------------------------------
     __device__ __forceinline__ void phase1(const BathyDev &b, const CurrentDev &c, double x, double y)
     {
@@ -593,14 +550,8 @@ struct FastRay {
                 iy = __fdiv_rn(__fsub_rn(yf, b.yf0), b.sy);
             }
             ok = ix >= 0.0f && ix <= b.nxm1f && iy >= 0.0f && iy <= b.nym1f;      // :291
-            if (UNI && MR_MAGIC_FLOOR) {
-                const f32x2 t = add2_rm(pk(ix, iy), pk(kMagicF, kMagicF));
-                bx1 = clamp_cell((int)(unsigned)t, b.nx); by1 = clamp_cell((int)(unsigned)(t >> 32), b.ny);
-                brec = b.cell + 2u * ((unsigned)(b.nx - 1) * (unsigned)by1 + (unsigned)bx1 - (unsigned)kMagicBits * (unsigned)b.nx);
-            } else {
-                bx1 = cell_of(ix, b.nx); by1 = cell_of(iy, b.ny);
-                brec = b.cell + 2u * (unsigned)((b.nx - 1) * by1 + bx1);
-            }
+            bx1 = cell_of(ix, b.nx); by1 = cell_of(iy, b.ny);
+            brec = b.cell + 2u * (unsigned)((b.nx - 1) * by1 + bx1);
         }
         if (CK == MR_CURRENT_GRID) {
             // f64 fractional index (cartesian_current.rs:246).  The spacing is a launch constant:
@@ -615,14 +566,8 @@ struct FastRay {
             const double ix = fma(fma(-qx, c.sx, tx), c.inv_sx, qx);
             const double iy = fma(fma(-qy, c.sy, ty), c.inv_sy, qy);
             ok = ok && ix >= 0.0 && ix <= c.nxm1d && iy >= 0.0 && iy <= c.nym1d;  // :248
-            if (UNI && MR_MAGIC_FLOOR) {
-                cx1 = clamp_cell(__double2loint(__dadd_rd(ix, kMagicD)), c.nx);
-                cy1 = clamp_cell(__double2loint(__dadd_rd(iy, kMagicD)), c.ny);
-                ccell = (unsigned)(c.nx - 1) * (unsigned)cy1 + (unsigned)cx1 - (unsigned)kMagicBits * (unsigned)c.nx;
-            } else {
-                cx1 = cell_of(ix, c.nx); cy1 = cell_of(iy, c.ny);
-                ccell = (unsigned)((c.nx - 1) * cy1 + cx1);
-            }
+            cx1 = cell_of(ix, c.nx); cy1 = cell_of(iy, c.ny);
+            ccell = (unsigned)((c.nx - 1) * cy1 + cx1);
         }
     }
 
@@ -673,7 +618,7 @@ struct FastRay {
             if (UNI) {
                 // corner coordinates (xa,ya) = i*d + p0 and (xb,yb) = (xa,ya) + d, then
                 // (Y, X) = (c10, c01) * ((x,y) - (xa,ya)), two components per instruction
-                const f32x2 pa = fma2(cell_f2(bx1, by1), b.d2, b.p0), pb = add2(pa, b.d2);
+                const f32x2 pa = fma2(pk((float)bx1, (float)by1), b.d2, b.p0), pb = add2(pa, b.d2);
                 const f32x2 yx = mul2(b.c2, sub2(p, pa));
                 bxa = lo_of(pa); bya = hi_of(pa); bxb = lo_of(pb); byb = hi_of(pb);
                 Y = lo_of(yx); X = hi_of(yx);
@@ -688,7 +633,7 @@ struct FastRay {
             if (xf == bxa || xf == bxb) {
                 const bool at_ya = yf == bya, at_yb = yf == byb;
                 if (at_ya || at_yb)
-                    h32 = corner_pick(h32, xf == bxa, xf == bxb, at_ya, at_yb, b.depth + (size_t)b.nx * cell_i(by1) + cell_i(bx1), b.nx);
+                    h32 = corner_pick(h32, xf == bxa, xf == bxb, at_ya, at_yb, b.depth + (size_t)b.nx * by1 + bx1, b.nx);
             }
             dhdx = gh.x; dhdy = gh.y;
         } else {
@@ -700,7 +645,7 @@ struct FastRay {
         if (CK == MR_CURRENT_GRID) {
             float X, Y;
             if (UNI) {
-                const f32x2 pa = fma2(cell_f2(cx1, cy1), c.d2, c.p0), pb = add2(pa, c.d2);
+                const f32x2 pa = fma2(pk((float)cx1, (float)cy1), c.d2, c.p0), pb = add2(pa, c.d2);
                 const f32x2 yx = mul2(c.c2, sub2(p, pa));
                 cxa = lo_of(pa); cya = hi_of(pa); cxb = lo_of(pb); cyb = hi_of(pb);
                 Y = lo_of(yx); X = hi_of(yx);
@@ -725,7 +670,7 @@ struct FastRay {
             if (xf == cxa || xf == cxb) {
                 const bool at_ya = yf == cya, at_yb = yf == cyb;
                 if (at_ya || at_yb) {
-                    const size_t node = (size_t)c.nx * cell_i(cy1) + cell_i(cx1);
+                    const size_t node = (size_t)c.nx * cy1 + cx1;
                     u32 = corner_pick(u32, xf == cxa, xf == cxb, at_ya, at_yb, c.u + node, c.nx);
                     v32 = corner_pick(v32, xf == cxa, xf == cxb, at_ya, at_yb, c.v + node, c.nx);
                 }

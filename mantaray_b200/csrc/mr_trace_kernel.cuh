@@ -38,15 +38,9 @@ struct TraceArgs {
     int64_t ld;
     int32_t *rows, *len;       // [n] or NULL
     double *fin;               // [4][n] or NULL
-    // filled by launch_trace_math: the stage offsets {0, dt/2, dt/2, dt} of the RK4 loop, read with the
-    // stage number as a constant-bank index (one LDC instead of compares and selects per stage)
-    double stage_a[4];
-    // and the trajectory planes as byte offsets from the x plane, the row pitch in bytes
+    // filled by launch_trace_math: the trajectory planes as byte offsets from the x plane, the row pitch in bytes
     int64_t off_y, off_kx, off_ky, row_bytes;
 };
-
-// RK4 weights {1, 2, 2, 1} of the stage derivatives, indexed the same way
-static __constant__ double kStageW[4] = {1.0, 2.0, 2.0, 1.0};
 
 static constexpr int kBlock = kBlockThreads;
 
@@ -61,14 +55,6 @@ static constexpr int kBlock = kBlockThreads;
 // grids whose f32 coordinates are not affine keep the per-cell corner coordinates and basis live: more registers
 #ifndef MR_MIN_BLOCKS_GENERIC
 #define MR_MIN_BLOCKS_GENERIC 5
-#endif
-// stage offsets and weights read from tables indexed by the stage number (0: computed with selects)
-#ifndef MR_STAGE_TABLE
-#define MR_STAGE_TABLE 0
-#endif
-// the RK4 loop as one flattened (step, stage) loop (1) or as a stage loop nested in a step loop (0)
-#ifndef MR_FLAT_LOOP
-#define MR_FLAT_LOOP 0
 #endif
 static constexpr int kStageUnroll = MR_STAGE_UNROLL;
 // (Two rays per thread — interleaved RHS phases, 16-byte row stores — was measured at 2.0e10 ray-steps/s
@@ -104,24 +90,22 @@ __device__ __forceinline__ void store_fin(const TraceArgs &a, const double y[4])
     const int64_t i = ray_index(a);
     a.fin[i] = y[0]; a.fin[a.n + i] = y[1]; a.fin[2 * a.n + i] = y[2]; a.fin[3 * a.n + i] = y[3];
 }
+__device__ __forceinline__ void store_count(const TraceArgs &a, int32_t *dst, int32_t v)
+{
+    dst[ray_index(a)] = v;
+}
 
-// FIN: the last NaN-free state of every ray is wanted (a.fin).  It is a template parameter because the
-// state it needs — y of the row before the first NaN — is otherwise dead once the next row exists: without
-// it the new row is formed in place, with it every step ends in a register-to-register copy of the state.
-//
 // Per-ray bookkeeping is event-driven: `rows` is written when the ray stops and `len` when its first NaN
 // appears (each at most once per ray, re-deriving the ray index on the spot), so the step loop carries two
 // flags and one row pointer per thread; the step number and the store countdown are warp-uniform.
-template <int BK, int CK, int MATH, bool UNI, bool FIN>
+template <int BK, int CK, int MATH, bool UNI>
 __global__ void __launch_bounds__(kBlock, (MATH == MR_MATH_FAST) ? (UNI ? MR_MIN_BLOCKS : MR_MIN_BLOCKS_GENERIC) : 1)
 trace_kernel(const __grid_constant__ TraceArgs a)
 {
     const bool store = a.x != nullptr;
     const double dt = a.dt;
     const double sixth = dt / 6.0;
-#if !MR_STAGE_TABLE
     const double half = dt / 2.0;
-#endif
     const int32_t nsteps = (int32_t)a.nsteps;      // < 2^31 (mr_num_steps)
 
     double y[1][4];
@@ -134,96 +118,29 @@ trace_kernel(const __grid_constant__ TraceArgs a)
     bool alive = nsteps > 0;
     bool clean = !any_nan4(y[0]);          // no NaN seen yet: rows so far all count towards len
     if (!clean) {                          // no NaN-free row at all
-        if (a.len) a.len[ray_index(a)] = 0;
-        if (FIN && a.fin) { const double nanrow[4] = {qnan(), qnan(), qnan(), qnan()}; store_fin(a, nanrow); }
+        if (a.len) store_count(a, a.len, 0);
+        if (a.fin) { const double nanrow[4] = {qnan(), qnan(), qnan(), qnan()}; store_fin(a, nanrow); }
     }
     if (store) store_row(a, p, y[0]);
 
     int32_t until_store = a.stride;        // counts down to the next stored row
-#if MR_FLAT_LOOP
-    // The RK4 loop, flattened: ONE loop over (step, stage) whose body is a stage; the step's bookkeeping runs
-    // when stage 3 has been evaluated.  (As a stage loop nested in a step loop, ptxas re-loaded the ~30
-    // uniform registers of launch constants at the top of every step: it hoists them out of one loop only.)
-    double k[1][4], acc[4];
-    bool k0_nan = false;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) { k[0][c] = 0.0; acc[c] = -0.0; }    // -0 + k0 == k0 for every k0
-    int32_t s = 1, st = 0;
-    while (s <= nsteps) {
-        if (alive) {
-#if MR_STAGE_TABLE
-            const double as = a.stage_a[st], ws = kStageW[st];
-#else
-            const double as = (st == 0) ? 0.0 : (st == 3 ? dt : half);
-            const double ws = (st == 1 || st == 2) ? 2.0 : 1.0;
-#endif
-            double yt[1][4];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const double adv = (MATH == MR_MATH_STRICT) ? __dadd_rn(y[0][c], __dmul_rn(k[0][c], as)) : fma(k[0][c], as, y[0][c]);
-                // stage 0 evaluates f(y): k is 0 there, and y + 0*0 == y (a -0 component would become
-                // +0, which the strict path must not allow)
-                yt[0][c] = (MATH == MR_MATH_STRICT && st == 0) ? y[0][c] : adv;
-            }
-            rhs<BK, CK, MATH, UNI, 1>(a.b, a.c, yt, k);
-            if (st == 0) k0_nan = all_nan4(k[0]);
-#pragma unroll
-            for (int c = 0; c < 4; ++c)
-                acc[c] = (MATH == MR_MATH_STRICT) ? __dadd_rn(acc[c], __dmul_rn(k[0][c], ws)) : fma(k[0][c], ws, acc[c]);
-        }
-        if (++st < 4) continue;
-        // ---- all four stages done: the new row ----
-        st = 0;
-        if (alive) {
-            double yn[4];
-#pragma unroll
-            for (int c = 0; c < 4; ++c)
-                yn[c] = (MATH == MR_MATH_STRICT) ? __dadd_rn(y[0][c], __dmul_rn(acc[c], sixth)) : fma(acc[c], sixth, y[0][c]);
-            const bool n0 = isnan(yn[0]), n1 = isnan(yn[1]), n2 = isnan(yn[2]), n3 = isnan(yn[3]);
-            if (clean && (n0 || n1 || n2 || n3)) {       // first NaN: rows 0..s-1 are the NaN-free ones
-                clean = false;
-                if (a.len) a.len[ray_index(a)] = s;
-                if (FIN && a.fin) store_fin(a, y[0]);
-            }
-            if (k0_nan || (n0 && n1 && n2 && n3)) {       // solout: this row, s, is the ray's last
-                alive = false;
-                if (a.rows) a.rows[ray_index(a)] = s + 1;
-            }
-            // (a stopped ray's state is all-NaN from here on)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) { y[0][c] = yn[c]; k[0][c] = 0.0; acc[c] = -0.0; }
-        }
-        if (--until_store == 0) {
-            until_store = a.stride;
-            p += a.row_bytes;
-            if (store) store_row(a, p, y[0]);
-        }
-        ++s;
-#ifndef MR_X_NOVOTE
-        if (!__any_sync(0xffffffffu, alive)) break;
-#endif
-    }
-#else
-    // the RK4 loop as a stage loop nested in a step loop (A/B alternative to the flattened form)
     for (int32_t s = 1; s <= nsteps; ++s) {
         if (!__any_sync(0xffffffffu, alive)) break;
         if (alive) {
             double k[1][4], acc[4];
             bool k0_nan;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) { k[0][c] = 0.0; acc[c] = -0.0; }
+            for (int c = 0; c < 4; ++c) { k[0][c] = 0.0; acc[c] = -0.0; }    // -0 + k0 == k0 for every k0
 #pragma unroll kStageUnroll
             for (int st = 0; st < 4; ++st) {
-#if MR_STAGE_TABLE
-                const double as = a.stage_a[st], ws = kStageW[st];
-#else
                 const double as = (st == 0) ? 0.0 : (st == 3 ? dt : half);
                 const double ws = (st == 1 || st == 2) ? 2.0 : 1.0;
-#endif
                 double yt[1][4];
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     const double adv = (MATH == MR_MATH_STRICT) ? __dadd_rn(y[0][c], __dmul_rn(k[0][c], as)) : fma(k[0][c], as, y[0][c]);
+                    // stage 0 evaluates f(y): k is 0 there, and y + 0*0 == y (a -0 component would become
+                    // +0, which the strict path must not allow)
                     yt[0][c] = (MATH == MR_MATH_STRICT && st == 0) ? y[0][c] : adv;
                 }
                 rhs<BK, CK, MATH, UNI, 1>(a.b, a.c, yt, k);
@@ -239,12 +156,12 @@ trace_kernel(const __grid_constant__ TraceArgs a)
             const bool n0 = isnan(yn[0]), n1 = isnan(yn[1]), n2 = isnan(yn[2]), n3 = isnan(yn[3]);
             if (clean && (n0 || n1 || n2 || n3)) {
                 clean = false;
-                if (a.len) a.len[ray_index(a)] = s;
-                if (FIN && a.fin) store_fin(a, y[0]);
+                if (a.len) store_count(a, a.len, s);
+                if (a.fin) store_fin(a, y[0]);        // y, the row before this one, is the last NaN-free state
             }
             if (k0_nan || (n0 && n1 && n2 && n3)) {
                 alive = false;
-                if (a.rows) a.rows[ray_index(a)] = s + 1;
+                if (a.rows) store_count(a, a.rows, s + 1);
             }
 #pragma unroll
             for (int c = 0; c < 4; ++c) y[0][c] = yn[c];
@@ -255,7 +172,6 @@ trace_kernel(const __grid_constant__ TraceArgs a)
             if (store) store_row(a, p, y[0]);
         }
     }
-#endif
     // whole warp stopped early: the rows it never reached are NaN (how many is read off the row pointer,
     // so that nothing but the pointer is carried through the loop for it)
     if (store) {
@@ -269,22 +185,21 @@ trace_kernel(const __grid_constant__ TraceArgs a)
     // a ray still integrating when the loop ends ran all nsteps (nsteps == 0: the initial row only);
     // one that never met a NaN is still integrating, so its len is its rows
     if (alive || nsteps <= 0) {
-        if (a.rows) a.rows[ray_index(a)] = nsteps + 1;
+        if (a.rows) store_count(a, a.rows, nsteps + 1);
     }
     if (clean) {
-        if (a.len) a.len[ray_index(a)] = nsteps + 1;
-        if (FIN && a.fin) store_fin(a, y[0]);
+        if (a.len) store_count(a, a.len, nsteps + 1);
+        if (a.fin) store_fin(a, y[0]);
     }
 }
 
-// One instantiation per (bathymetry kind, current kind[, affine grids]) and per FIN; the kinds are
-// uniform over a launch, so the dispatch is a host-side switch.
+// One instantiation per (bathymetry kind, current kind[, affine grids]); the kinds are uniform over a
+// launch, so the dispatch is a host-side switch.
 template <int MATH>
 static cudaError_t launch_trace_math(const TraceArgs &args, cudaStream_t stream)
 {
     if (args.n <= 0) return cudaSuccess;
     TraceArgs a = args;
-    a.stage_a[0] = 0.0; a.stage_a[1] = a.stage_a[2] = a.dt / 2.0; a.stage_a[3] = a.dt;
     a.off_y = (const char *)a.y - (const char *)a.x; a.off_kx = (const char *)a.kx - (const char *)a.x;
     a.off_ky = (const char *)a.ky - (const char *)a.x; a.row_bytes = a.ld * (int64_t)sizeof(double);
     // the fast path's affine-coordinate specialisation needs every gridded field to qualify
@@ -293,13 +208,7 @@ static cudaError_t launch_trace_math(const TraceArgs &args, cudaStream_t stream)
                      (a.b.kind == MR_BATHY_GRID || a.c.kind == MR_CURRENT_GRID);
     const unsigned grid = (unsigned)((a.n + (int64_t)kBlock - 1) / (int64_t)kBlock);
     constexpr bool kFast = MATH == MR_MATH_FAST;
-    // the strict kernels are compiled with FIN only (and test a.fin at run time)
-    const bool fin = !kFast || a.fin != nullptr;
-#define MR_LAUNCH(BKV, CKV, UNIV)                                                                              \
-    do {                                                                                                       \
-        if (fin) trace_kernel<BKV, CKV, MATH, UNIV, true><<<grid, kBlock, 0, stream>>>(a);                     \
-        else trace_kernel<BKV, CKV, MATH, UNIV, !kFast><<<grid, kBlock, 0, stream>>>(a);                       \
-    } while (0)
+#define MR_LAUNCH(BKV, CKV, UNIV) trace_kernel<BKV, CKV, MATH, UNIV><<<grid, kBlock, 0, stream>>>(a)
 #define MR_CASE(BKV, CKV)                                                                                      \
     if (a.b.kind == BKV && a.c.kind == CKV) {                                                                  \
         if (uni) MR_LAUNCH(BKV, CKV, kFast);                                                                   \

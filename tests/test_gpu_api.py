@@ -206,3 +206,71 @@ def test_work_buffers_are_reused_and_trimmed(gpu):
     # a failed call (out of memory) leaves the handle usable and holds nothing
     with Fields(wl.bathymetry, wl.current, devices=[0]) as f:
         same(trace_many(f, *rays, wl.t0, wl.duration, wl.dt), first)
+
+
+@pytest.mark.parametrize("math", [_abi.MR_MATH_FAST, _abi.MR_MATH_STRICT])
+@pytest.mark.parametrize("stride", [1, 7])
+def test_device_entry_point_with_scattered_planes_pitch_and_optional_outputs(oracle, gpu, math, stride):
+    """mr_trace_device on caller-owned device buffers: the four planes are separate allocations in arbitrary
+    address order (the kernel reaches y, kx, ky through byte offsets from the x plane, negative ones included),
+    the pitch exceeds n, n is not a multiple of the block size (the last block's spare threads repeat the last
+    ray), and rows / len / final are each optional.  Everything outside the n used columns and the stored rows
+    must keep its sentinel; everything inside must match the oracle (some rays leave the domain early, so
+    whole warps stop and NaN-fill)."""
+    import torch
+
+    wl = W.c2_sea_mount(1000, 700, half=300)
+    x0, y0, kx0, ky0 = wl.all_rays()
+    n = x0.size
+    assert n % 128 != 0
+    ref = oracle.trace_many(wl.bathymetry, wl.current, x0, y0, kx0, ky0, 0.0, wl.duration, wl.dt, stride=stride)
+    rows_cap = ref.x.shape[0]
+    dev = torch.device("cuda", 0)
+    ld, guard, sent = n + 37, 3, -777.25
+    lib = _capi.load()
+    with Fields(wl.bathymetry, wl.current, devices=[0]) as f:
+        ic = torch.from_numpy(np.stack([x0, y0, kx0, ky0])).to(dev)
+        # allocate ky first and x last: with torch's caching allocator the planes end up in no particular order
+        planes = {}
+        for name in ("ky", "y", "kx", "x"):
+            planes[name] = torch.full((rows_cap + guard, ld), sent, dtype=torch.float64, device=dev)
+        d_rows = torch.full((n + 5,), -9, dtype=torch.int32, device=dev)
+        d_len = torch.full((n + 5,), -9, dtype=torch.int32, device=dev)
+        d_fin = torch.full((4, n), sent, dtype=torch.float64, device=dev)
+        opts = _abi.TraceOpts(stride, math, 0, 0)
+        st = torch.cuda.current_stream()
+        p = lambda t: C.c_void_p(t.data_ptr())
+
+        def run(rows, length, fin):
+            rc = lib.mr_trace_device(f.handle, 0, C.c_void_p(st.cuda_stream), n, p(ic[0]), p(ic[1]), p(ic[2]), p(ic[3]),
+                                     0.0, wl.duration, wl.dt, C.byref(opts), p(planes["x"]), p(planes["y"]),
+                                     p(planes["kx"]), p(planes["ky"]), ld, rows, length, fin, None)
+            assert rc == 0, lib.mr_last_error()
+            torch.cuda.synchronize()
+
+        run(p(d_rows), p(d_len), p(d_fin))
+        got = {k: v.cpu().numpy() for k, v in planes.items()}
+        for name in ("x", "y", "kx", "ky"):
+            a = got[name]
+            assert (a[rows_cap:] == sent).all(), f"{name}: rows past the last stored row were written"
+            assert (a[:, n:] == sent).all(), f"{name}: columns past the last ray were written"
+        res = oracle.Result(ref.t, got["x"][:rows_cap, :n], got["y"][:rows_cap, :n], got["kx"][:rows_cap, :n],
+                            got["ky"][:rows_cap, :n], d_rows.cpu().numpy()[:n], d_len.cpu().numpy()[:n], None, stride)
+        assert_parity(res, ref, what=f"device entry point math={math} stride={stride}")
+        assert (d_rows.cpu().numpy()[n:] == -9).all() and (d_len.cpu().numpy()[n:] == -9).all()
+        fin = d_fin.cpu().numpy()
+        assert ref.rows.min() < ref.rows.max(), "the case should contain rays that stop early"
+        # final state = the last NaN-free state, stored row or not; with stride 1 it is row len-1 of the trajectory
+        np.testing.assert_array_equal(np.isnan(fin), np.isnan(ref.final_state))
+        np.testing.assert_allclose(fin[:2], ref.final_state[:2], rtol=0, atol=1e-9 * np.nanmax(np.abs(ref.final_state[:2])))
+        np.testing.assert_allclose(fin[2:], ref.final_state[2:], rtol=0, atol=1e-9 * np.nanmax(np.abs(ref.final_state[2:])))
+        if stride == 1:
+            last = res.len - 1
+            for j, name in enumerate(("x", "y", "kx", "ky")):
+                np.testing.assert_array_equal(fin[j], got[name][last, np.arange(n)])
+        # the same launch without the optional outputs leaves the planes identical
+        for k in planes.values():
+            k[:rows_cap, :n] = 0.0
+        run(None, None, None)
+        for name in ("x", "y", "kx", "ky"):
+            np.testing.assert_array_equal(planes[name].cpu().numpy(), got[name])

@@ -36,6 +36,29 @@ METRIC = "fp64_ray_steps_per_sec"
 UNIT = "ray-steps/s"
 
 
+# The contract is ONE JSON line on stdout.  Libraries print there too (NCCL announces its version on the
+# first communicator), so file descriptor 1 is pointed at stderr for the whole run and the line is written
+# to the saved descriptor.
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        os.write(1, data)
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -198,11 +221,12 @@ def run_reference(args):
         "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
     args = parse()
+    claim_stdout()
     if args.impl == "reference":
         return run_reference(args)
 
@@ -416,7 +440,7 @@ def main():
             "roofline": roofline, "roofline_hbm": roofline_hbm,
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": n_launch_total, "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     fields.free()
     if world > 1:
         dist.destroy_process_group()

@@ -119,8 +119,14 @@ typedef struct mr_trace_opts {
     int32_t stride;       /* store every stride-th row (row j = step j*stride); 1 = reference; 0 -> 1 */
     int32_t math;         /* MR_MATH_FAST (default) or MR_MATH_STRICT                                 */
     int32_t chunk_rays;   /* host path: rays per device slab (0 = automatic)                          */
-    int32_t reserved;
+    int32_t flags;        /* MR_OPT_* bits; 0 = defaults                                              */
 } mr_trace_opts;
+
+/* MR_MATH_FAST on affine gridded bathymetry: skip the depth lookup wherever a per-block lower bound of
+ * the depth already proves kh >= 22, where the reference's own formulas no longer depend on h (see
+ * DESIGN.md).  Same rows / len; values equal to the unflagged fast path up to the sign of an exact zero.
+ * Off by default in this round (measured, not yet run through the whole parity suite). */
+#define MR_OPT_DEEP_MAP 1
 
 /* ---- library ------------------------------------------------------------- */
 

@@ -70,6 +70,9 @@ class CurrentDesc(C.Structure):
     ]
 
 
+MR_OPT_DEEP_MAP = 1
+
+
 class TraceOpts(C.Structure):
     """``mr_trace_opts``"""
 
@@ -77,7 +80,7 @@ class TraceOpts(C.Structure):
         ("stride", C.c_int32),
         ("math", C.c_int32),
         ("chunk_rays", C.c_int32),
-        ("reserved", C.c_int32),
+        ("flags", C.c_int32),
     ]
 
 

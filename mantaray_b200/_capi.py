@@ -242,15 +242,16 @@ def num_steps(t0: float, t_end: float, dt: float) -> int:
     return n
 
 
-def _opts(stride: int, math: int, chunk_rays: int) -> _abi.TraceOpts:
-    return _abi.TraceOpts(int(stride), int(math), int(chunk_rays), 0)
+def _opts(stride: int, math: int, chunk_rays: int, flags: int = 0) -> _abi.TraceOpts:
+    return _abi.TraceOpts(int(stride), int(math), int(chunk_rays), int(flags))
 
 
 def trace_many(fields: Fields, x0, y0, kx0, ky0, t0: float, t_end: float, dt: float, *,
                stride: int = 1, math: int = _abi.MR_MATH_FAST, chunk_rays: int = 0,
                trajectories: bool = True, final_state: bool = False, pinned: Optional[bool] = False,
-               env: bool = False) -> TraceResult:
-    """``mr_trace_many`` on numpy arrays; ``env=True`` adds depth, u, v at every stored row (``mr_trace_many_env``)."""
+               env: bool = False, flags: int = 0) -> TraceResult:
+    """``mr_trace_many`` on numpy arrays; ``env=True`` adds depth, u, v at every stored row (``mr_trace_many_env``);
+    ``flags`` are the ``MR_OPT_*`` bits of ``mr_trace_opts``."""
     lib = load()
     x0 = np.ascontiguousarray(x0, dtype=np.float64).ravel()
     y0 = np.ascontiguousarray(y0, dtype=np.float64).ravel()
@@ -280,7 +281,7 @@ def trace_many(fields: Fields, x0, y0, kx0, ky0, t0: float, t_end: float, dt: fl
     rows = np.empty(n, dtype=np.int32)
     length = np.empty(n, dtype=np.int32)
     fin = np.empty((4, n), dtype=np.float64) if final_state else None
-    o = _opts(stride, math, chunk_rays)
+    o = _opts(stride, math, chunk_rays, flags)
     ptr = lambda a: a.ctypes.data if a is not None else None
     if env:
         if not trajectories:

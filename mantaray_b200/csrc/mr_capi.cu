@@ -12,6 +12,7 @@
 // device copying its column block of the step-major [rows][n] host arrays.
 #include <cuda_runtime.h>
 
+#include <cfloat>
 #include <cmath>
 #include <chrono>
 #include <cstdio>
@@ -241,6 +242,41 @@ static bool affine_f32(const float *c, int n, float *d_out)
     return true;
 }
 
+// Depth-floor map of the fast path (FastRay, DMAP): for every block of kDeepBlock x kDeepBlock cells, the square
+// (rounded down) of H = zmin - 1e-5 zmax over the f32 depths of all nodes the block's cells touch.  The f32
+// bilinear of interpolator.rs:59-83 returns, inside a cell, a value between its corners up to a few roundings of
+// terms no larger than ~2 zmax (< 1e-6 zmax), so every depth the lookup can produce in the block is >= H.
+// A block with a node that is NaN, infinite or <= 0 gets 0: no bound, the kernel looks the depth up.
+static std::vector<float> depth_floor_map(const double *depth, int nx, int ny, int *nbx_out, int *nby_out)
+{
+    const int B = kDeepBlock;
+    const int nbx = (nx - 1 + B - 1) / B, nby = (ny - 1 + B - 1) / B;
+    std::vector<float> out((size_t)nbx * (size_t)nby, 0.0f);
+    for (int by = 0; by < nby; ++by) {
+        const int j0 = by * B, j1 = std::min(j0 + B, ny - 1);          // nodes j0..j1 inclusive
+        for (int bx = 0; bx < nbx; ++bx) {
+            const int i0 = bx * B, i1 = std::min(i0 + B, nx - 1);
+            float zmin = INFINITY, zmax = 0.0f;
+            bool bad = false;
+            for (int j = j0; j <= j1 && !bad; ++j)
+                for (int i = i0; i <= i1; ++i) {
+                    const float z = (float)depth[(size_t)j * (size_t)nx + (size_t)i];   // `as f32`, cartesian_netcdf3.rs:426
+                    if (!(z > 0.0f) || std::isinf(z)) { bad = true; break; }
+                    zmin = std::min(zmin, z); zmax = std::max(zmax, z);
+                }
+            if (bad) continue;
+            const double H = (double)zmin - 1e-5 * (double)zmax;
+            if (!(H > 0.0)) continue;
+            const double sq = H * H;
+            float v = sq >= (double)FLT_MAX ? FLT_MAX : (float)sq;
+            if ((double)v > sq) v = std::nextafterf(v, 0.0f);
+            out[(size_t)by * (size_t)nbx + (size_t)bx] = v;
+        }
+    }
+    *nbx_out = nbx; *nby_out = nby;
+    return out;
+}
+
 // change-of-basis coefficients of interpolator.rs:64-72 for a (dx, dy) cell, in f32
 static bool basis_coeffs(float dx, float dy, float *c01, float *c10)
 {
@@ -311,6 +347,13 @@ static int upload_fields(DeviceFields &d, const mr_bathymetry_desc *b, const mr_
                     basis_coeffs(B.dxf, B.dyf, &B.c01, &B.c10);
         B.p0 = pack2(B.xf0, B.yf0); B.rs2 = pack2(B.rsx, B.rsy); B.ns2 = pack2(-B.sx, -B.sy);
         B.d2 = pack2(B.dxf, B.dyf); B.c2 = pack2(B.c10, B.c01);
+        B.dmap = nullptr; B.dmap_nbx = 0;
+        if (B.uniform) {
+            int nbx = 0, nby = 0;
+            std::vector<float> dm = depth_floor_map(b->depth, b->nx, b->ny, &nbx, &nby);
+            if ((rc = upload(d, dm.data(), dm.size(), &B.dmap))) return rc;
+            B.dmap_nbx = nbx;
+        }
     } else if (b->kind == MR_BATHY_ARRAY) {
         int rc;
         if ((rc = upload(d, b->array, (size_t)b->nx * b->ny, &B.array))) return rc;
@@ -395,7 +438,7 @@ static const DeviceFields *find_device(const mr_fields *f, int dev)
 
 static void normalise_opts(const mr_trace_opts *in, mr_trace_opts &o)
 {
-    o = mr_trace_opts{1, MR_MATH_FAST, 0, 0};
+    o = mr_trace_opts{1, MR_MATH_FAST, 0, 0};       // stride, math, chunk_rays, flags
     if (in) o = *in;
     if (o.stride <= 0) o.stride = 1;
 }
@@ -412,6 +455,7 @@ static int enqueue_trace(const DeviceFields &d, cudaStream_t stream, int64_t n,
     a.dt = dt; a.nsteps = nsteps; a.stride = o.stride;
     a.x = x; a.y = y; a.kx = kx; a.ky = ky; a.ld = ld;
     a.rows = rows; a.len = len; a.fin = fin;
+    a.deep_map = (o.flags & MR_OPT_DEEP_MAP) != 0;
     cudaError_t e;
     if (o.math == MR_MATH_STRICT) e = launch_trace_strict(a, stream);
     else if (o.math == MR_MATH_FAST) e = launch_trace_fast(a, stream);
@@ -564,6 +608,7 @@ static int trace_block_on_device(DeviceFields &d, const HostJob &j, int64_t lo, 
                 a.x = tx; a.y = tx ? tx + plane : nullptr; a.kx = tx ? tx + 2 * plane : nullptr; a.ky = tx ? tx + 3 * plane : nullptr;
                 a.ld = chunk;
                 a.rows = B.rows; a.len = B.len; a.fin = B.fin;
+                a.deep_map = (j.o.flags & MR_OPT_DEEP_MAP) != 0;
                 // fin is [4][n] with n = m for the kernel (it uses a.n as the pitch)
                 cudaError_t e = j.o.math == MR_MATH_STRICT ? launch_trace_strict(a, s_comp) : launch_trace_fast(a, s_comp);
                 if (e != cudaSuccess) { rc = bail(MR_ERR_CUDA, std::string("trace kernel launch: ") + cudaGetErrorString(e)); goto done; }

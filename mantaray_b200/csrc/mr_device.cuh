@@ -58,7 +58,14 @@ struct BathyDev {
     float dxf, dyf, c01, c10;
     // the same constants as (x, y) pairs for the packed f32 path
     f32x2 p0, rs2, ns2, d2, c2;   // {x0,y0} {1/sx,1/sy} {-sx,-sy} {dx,dy} {c10,c01}
+    // depth-floor map (see FastRay, DMAP): per block of kDeepBlock x kDeepBlock cells, the square of a lower
+    // bound of every depth the f32 bilinear can return anywhere in the block (0: no bound, e.g. a dry or
+    // non-finite node); [dmap_nby][dmap_nbx] floats, row-major
+    const float *dmap;
+    int32_t dmap_nbx;
 };
+static constexpr int kDeepShift = 3;                 // log2 of the block side, in cells
+static constexpr int kDeepBlock = 1 << kDeepShift;
 
 struct CurrentDev {
     int32_t kind;
@@ -233,6 +240,15 @@ __device__ __forceinline__ void ldg_f4_d2(const float4 *p, float4 &a, double2 &b
 {
     unsigned long long q0, q1;
     asm volatile("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(q0), "=l"(q1), "=d"(b.x), "=d"(b.y) : "l"(p));
+    a.x = __uint_as_float((unsigned)q0); a.y = __uint_as_float((unsigned)(q0 >> 32));
+    a.z = __uint_as_float((unsigned)q1); a.w = __uint_as_float((unsigned)(q1 >> 32));
+}
+// the same load, skipped by the lanes that do not need the record (a and b keep whatever their registers held)
+__device__ __forceinline__ void ldg_f4_d2_unless(bool skip, const float4 *p, float4 &a, double2 &b)
+{
+    unsigned long long q0, q1;
+    asm volatile("{ .reg .pred q; setp.eq.s32 q, %5, 0; @q ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4]; }"
+                 : "=l"(q0), "=l"(q1), "=d"(b.x), "=d"(b.y) : "l"(p), "r"((int)skip));
     a.x = __uint_as_float((unsigned)q0); a.y = __uint_as_float((unsigned)(q0 >> 32));
     a.z = __uint_as_float((unsigned)q1); a.w = __uint_as_float((unsigned)(q1 >> 32));
 }
@@ -455,13 +471,12 @@ __device__ __forceinline__ void exp_expm1_neg(double z, double &E, double &em)
 // k == 0, k NaN) reaches this function as h = NaN and leaves it as four NaNs by plain NaN
 // propagation, so there is no per-output select.  Large kh: E -> 0, tanh = 1, second cg term
 // 0, bathymetric term -0 (the reference gets the same from cosh^2 -> inf and sinh -> inf).
-__device__ __forceinline__ void rhs_f64_fast(double kx, double ky, double k, double cs, double sn,
-                                             double h, double dhdx, double dhdy,
-                                             const CurrentVal &cv, double out[4])
+// cg and the factor (bx, by) = Bc grad(h) of dk/dt, from (k, h, grad h).
+__device__ __forceinline__ void wave_terms(double k, double h, double dhdx, double dhdy,
+                                           double &cg, double &bx, double &by)
 {
     const double kh = k * h;
-    // cg and the factor Bc of grad(h) in dk/dt; tanh kh = T, kh/cosh^2 kh = hs2, 1/(sinh kh cosh kh) = csch_sech
-    double cg, bx, by;
+    // tanh kh = T, kh/cosh^2 kh = hs2, 1/(sinh kh cosh kh) = csch_sech
     if (!(kh >= kExpRed[4])) {
         double E, em;
         exp_expm1_neg(-2.0 * kh, E, em);
@@ -492,10 +507,33 @@ __device__ __forceinline__ void rhs_f64_fast(double kx, double ky, double k, dou
         cg = fma(kExpRed[6], rq, z);
         bx = -zk * dhdx; by = -zk * dhdy;
     }
+}
+// The same for a point already known to lie in deep water over finite, positive depths (depth-floor map):
+// the deep-water branch above with h and grad(h) finite, i.e. z = zk and -zk * grad(h) = -zk up to the
+// sign of an exact zero.  k NaN (k^2 infinite) still turns everything NaN.
+__device__ __forceinline__ void wave_terms_deep(double k, double &cg, double &bx, double &by)
+{
+    const double zk = k * 0.0;
+    double sq, rq;
+    sqrt_rsqrt(k * kExpRed[5], sq, rq);
+    cg = fma(kExpRed[6], rq, zk);
+    bx = -zk; by = -zk;
+}
+__device__ __forceinline__ void assemble_rhs(double kx, double ky, double cs, double sn, double cg, double bx, double by,
+                                             const CurrentVal &cv, double out[4])
+{
     out[0] = fma(cg, cs, cv.u);
     out[1] = fma(cg, sn, cv.v);
     out[2] = fma(-ky, cv.dvdx, fma(-kx, cv.dudx, bx));
     out[3] = fma(-ky, cv.dvdy, fma(-kx, cv.dudy, by));
+}
+__device__ __forceinline__ void rhs_f64_fast(double kx, double ky, double k, double cs, double sn,
+                                             double h, double dhdx, double dhdy,
+                                             const CurrentVal &cv, double out[4])
+{
+    double cg, bx, by;
+    wave_terms(k, h, dhdx, dhdy, cg, bx, by);
+    assemble_rhs(kx, ky, cs, sn, cg, bx, by, cv, out);
 }
 
 // =============================================================================
@@ -515,10 +553,20 @@ __device__ __forceinline__ void rhs_f64_fast(double kx, double ky, double k, dou
 // carries NR rays runs each phase for all of them before the next (rhs_fast_n): the compiler then
 // has NR independent instruction streams to interleave, and the uniform work of a phase (constant
 // loads, loop control) is paid once per thread instead of once per ray.
-template <int BK, int CK, bool UNI>
+// DMAP (affine gridded bathymetry only): the depth lookup is skipped where it cannot matter.  For kh >= 22 the
+// f64 stage takes its deep-water branch, whose outputs do not depend on h or grad(h) at all (rhs_f64_fast).  A
+// small map gives, per block of 8 x 8 cells, the square of a lower bound H of every depth the lookup could
+// return there; k^2 H^2 >= 484 (with a margin that dwarfs the f32 roundings, 2e-5 relative) proves kh >= 22
+// without the cell record: no 32-byte sector fetched (the map's floats are shared by whole blocks of lanes),
+// no bilinear, no corner test.  Lanes that fail the test — shallow water, a dry or non-finite node in the
+// block, a failed lookup — load the record and proceed exactly as without the map.
+template <int BK, int CK, bool UNI, bool DMAP = false>
 struct FastRay {
+    static constexpr bool kDmap = DMAP && UNI && BK == MR_BATHY_GRID;
     float xf, yf;
     bool ok;
+    bool deep;
+    float hsq;
     int bx1, by1, cx1, cy1;
     const float4 *brec;
     unsigned ccell;
@@ -529,10 +577,12 @@ struct FastRay {
     double k2, k, cs, sn;
 
     // ---- phase 1: fractional indices and cell addresses ------------------------------------------
-    __device__ __forceinline__ void phase1(const BathyDev &b, const CurrentDev &c, double x, double y)
+    __device__ __forceinline__ void phase1(const BathyDev &b, const CurrentDev &c, double x, double y, double kx, double ky)
     {
         xf = (float)x; yf = (float)y;                                              // wave_ray_path.rs:122
         ok = true;
+        deep = false;
+        k2 = fma(kx, kx, ky * ky);
         if (BK == MR_BATHY_GRID) {
             float ix, iy;                                                          // cartesian_netcdf3.rs:289
             if (UNI) {
@@ -552,6 +602,9 @@ struct FastRay {
             ok = ix >= 0.0f && ix <= b.nxm1f && iy >= 0.0f && iy <= b.nym1f;      // :291
             bx1 = cell_of(ix, b.nx); by1 = cell_of(iy, b.ny);
             brec = b.cell + 2u * (unsigned)((b.nx - 1) * by1 + bx1);
+            if (kDmap)
+                asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(hsq)
+                             : "l"(b.dmap + (unsigned)((by1 >> kDeepShift) * b.dmap_nbx + (bx1 >> kDeepShift))));
         }
         if (CK == MR_CURRENT_GRID) {
             // f64 fractional index (cartesian_current.rs:246).  The spacing is a launch constant:
@@ -575,7 +628,14 @@ struct FastRay {
     __device__ __forceinline__ void phase2(const BathyDev &b, const CurrentDev &c)
     {
         if (BK == MR_BATHY_GRID) {
-            ldg_f4_d2(brec, Z, gh);
+            if (kDmap) {
+                // (a NaN or infinite k^2 fails or passes harmlessly: NaN compares false; k^2 = inf makes k NaN,
+                // and the deep-water branch turns that into four NaNs like the general one)
+                deep = ok && __fmul_rn((float)k2, hsq) >= 484.01f;
+                ldg_f4_d2_unless(deep, brec, Z, gh);
+            } else {
+                ldg_f4_d2(brec, Z, gh);
+            }
             if (!UNI) {
                 bxa = __ldg(b.x + bx1); bxb = __ldg(b.x + bx1 + 1);
                 bya = __ldg(b.y + by1); byb = __ldg(b.y + by1 + 1);
@@ -594,25 +654,15 @@ struct FastRay {
     // ---- phase 3: wavenumber-only f64 work, under the loads --------------------------------------
     __device__ __forceinline__ void phase3(double kx, double ky)
     {
-        k2 = fma(kx, kx, ky * ky);
         double rk;
         sqrt_rsqrt(k2, k, rk);
         cs = kx * rk; sn = ky * rk;
     }
 
     // ---- phase 4: f32 bilinears, then the f64 stage --------------------------------------------------
-    __device__ __forceinline__ void phase4(const BathyDev &b, const CurrentDev &c, double kx, double ky, double out[4])
+    // depth and its gradient at (xf, yf) from the loaded record / the analytic kinds
+    __device__ __forceinline__ void bathy_part(const BathyDev &b, f32x2 p, float &h32, double &dhdx, double &dhdy)
     {
-        // Scheduling fence.  ptxas places the first consumer of the bathymetry record ahead of the
-        // current record's loads (whose f64 address chain is longer), so a warp waited for one L2
-        // round trip, issued the other loads, and waited again (profiles/r1/g_*).  OR-ing in
-        // (bits of the current record) & 0 — a zero the compiler cannot see — changes no value but
-        // makes the first bathymetry consumer depend on both loads, so both are in flight first.
-        if (BK == MR_BATHY_GRID && CK == MR_CURRENT_GRID)
-            Z.x = __int_as_float(__float_as_int(Z.x) | (__float_as_int(U.x) & b.zero));
-        const f32x2 p = pk(xf, yf);
-        float h32;
-        double dhdx, dhdy;
         if (BK == MR_BATHY_GRID) {
             float X, Y;
             if (UNI) {
@@ -641,7 +691,11 @@ struct FastRay {
             bathy_analytic(BK, b, xf, yf, h32, gx32, gy32);
             dhdx = (double)gx32; dhdy = (double)gy32;
         }
-        CurrentVal cv;
+    }
+
+    // current and its gradients at (xf, yf)
+    __device__ __forceinline__ void current_part(const CurrentDev &c, f32x2 p, CurrentVal &cv)
+    {
         if (CK == MR_CURRENT_GRID) {
             float X, Y;
             if (UNI) {
@@ -680,6 +734,41 @@ struct FastRay {
         } else {
             cv.u = c.u0; cv.v = c.v0; cv.dudx = cv.dudy = cv.dvdx = cv.dvdy = 0.0;   // constant_current.rs:69-77
         }
+    }
+
+    __device__ __forceinline__ void phase4(const BathyDev &b, const CurrentDev &c, double kx, double ky, double out[4])
+    {
+        const f32x2 p = pk(xf, yf);
+        if (kDmap) {
+            // With the depth-floor map the current goes first: its record is what every lane waits for, and
+            // the lanes in proven deep water then go straight to the deep-water terms.
+            CurrentVal cv;
+            current_part(c, p, cv);
+            double cg, bx, by;
+            if (deep) {
+                wave_terms_deep(k, cg, bx, by);
+            } else {
+                float h32;
+                double dhdx, dhdy;
+                bathy_part(b, p, h32, dhdx, dhdy);
+                ok = ok && h32 > 0.0f;
+                wave_terms(k, (double)(ok ? h32 : qnanf()), dhdx, dhdy, cg, bx, by);
+            }
+            assemble_rhs(kx, ky, cs, sn, cg, bx, by, cv, out);
+            return;
+        }
+        // Scheduling fence.  ptxas places the first consumer of the bathymetry record ahead of the
+        // current record's loads (whose f64 address chain is longer), so a warp waited for one L2
+        // round trip, issued the other loads, and waited again (profiles/r1/g_*).  OR-ing in
+        // (bits of the current record) & 0 — a zero the compiler cannot see — changes no value but
+        // makes the first bathymetry consumer depend on both loads, so both are in flight first.
+        if (BK == MR_BATHY_GRID && CK == MR_CURRENT_GRID)
+            Z.x = __int_as_float(__float_as_int(Z.x) | (__float_as_int(U.x) & b.zero));
+        float h32;
+        double dhdx, dhdy;
+        bathy_part(b, p, h32, dhdx, dhdy);
+        CurrentVal cv;
+        current_part(c, p, cv);
         // h <= 0 -> cg = NaN and the bathymetric term is NaN too (inf*0 or sqrt of a negative): all four
         // NaN, like a failed lookup.  The depth is poisoned while still an f32 (one select, then the
         // conversion the path needs anyway).
@@ -694,13 +783,13 @@ struct FastRay {
 };
 
 // The RHS of NR rays carried by one thread, phase by phase.
-template <int BK, int CK, bool UNI, int NR>
+template <int BK, int CK, bool UNI, int NR, bool DMAP>
 __device__ __forceinline__ void rhs_fast_n(const BathyDev &b, const CurrentDev &c,
                                            const double (&s)[NR][4], double (&out)[NR][4])
 {
-    FastRay<BK, CK, UNI> ray[NR];
+    FastRay<BK, CK, UNI, DMAP> ray[NR];
 #pragma unroll
-    for (int r = 0; r < NR; ++r) ray[r].phase1(b, c, s[r][0], s[r][1]);
+    for (int r = 0; r < NR; ++r) ray[r].phase1(b, c, s[r][0], s[r][1], s[r][2], s[r][3]);
 #pragma unroll
     for (int r = 0; r < NR; ++r) ray[r].phase2(b, c);
 #pragma unroll
@@ -712,7 +801,7 @@ __device__ __forceinline__ void rhs_fast_n(const BathyDev &b, const CurrentDev &
 // =============================================================================
 // System::system (wave_ray_path.rs:220-234): Err -> four NaN
 // =============================================================================
-template <int BK, int CK, int MATH, bool UNI, int NR>
+template <int BK, int CK, int MATH, bool UNI, int NR, bool DMAP = false>
 __device__ __forceinline__ void rhs(const BathyDev &b, const CurrentDev &c,
                                     const double (&s)[NR][4], double (&out)[NR][4])
 {
@@ -733,7 +822,7 @@ __device__ __forceinline__ void rhs(const BathyDev &b, const CurrentDev &c,
             else rhs_f64_strict(kx, ky, (double)h32, (double)gx32, (double)gy32, cv, out[r]);
         }
     } else {
-        rhs_fast_n<BK, CK, UNI, NR>(b, c, s, out);
+        rhs_fast_n<BK, CK, UNI, NR, DMAP>(b, c, s, out);
     }
 }
 

@@ -38,8 +38,10 @@ struct TraceArgs {
     int64_t ld;
     int32_t *rows, *len;       // [n] or NULL
     double *fin;               // [4][n] or NULL
+    int32_t deep_map;          // use the bathymetry's depth-floor map where the grids allow it (MR_OPT_DEEP_MAP)
     // filled by launch_trace_math: the trajectory planes as byte offsets from the x plane, the row pitch in bytes
     int64_t off_y, off_kx, off_ky, row_bytes;
+    double sixth;              // dt / 6 (read from here by the depth-floor-map variant, which is short of registers)
 };
 
 static constexpr int kBlock = kBlockThreads;
@@ -55,6 +57,10 @@ static constexpr int kBlock = kBlockThreads;
 // grids whose f32 coordinates are not affine keep the per-cell corner coordinates and basis live: more registers
 #ifndef MR_MIN_BLOCKS_GENERIC
 #define MR_MIN_BLOCKS_GENERIC 5
+#endif
+// the depth-floor-map variant carries a little more state per thread
+#ifndef MR_MIN_BLOCKS_DMAP
+#define MR_MIN_BLOCKS_DMAP 7
 #endif
 static constexpr int kStageUnroll = MR_STAGE_UNROLL;
 // (Two rays per thread — interleaved RHS phases, 16-byte row stores — was measured at 2.0e10 ray-steps/s
@@ -98,13 +104,13 @@ __device__ __forceinline__ void store_count(const TraceArgs &a, int32_t *dst, in
 // Per-ray bookkeeping is event-driven: `rows` is written when the ray stops and `len` when its first NaN
 // appears (each at most once per ray, re-deriving the ray index on the spot), so the step loop carries two
 // flags and one row pointer per thread; the step number and the store countdown are warp-uniform.
-template <int BK, int CK, int MATH, bool UNI>
-__global__ void __launch_bounds__(kBlock, (MATH == MR_MATH_FAST) ? (UNI ? MR_MIN_BLOCKS : MR_MIN_BLOCKS_GENERIC) : 1)
+template <int BK, int CK, int MATH, bool UNI, bool DMAP>
+__global__ void __launch_bounds__(kBlock, (MATH == MR_MATH_FAST) ? (UNI ? (DMAP ? MR_MIN_BLOCKS_DMAP : MR_MIN_BLOCKS) : MR_MIN_BLOCKS_GENERIC) : 1)
 trace_kernel(const __grid_constant__ TraceArgs a)
 {
     const bool store = a.x != nullptr;
     const double dt = a.dt;
-    const double sixth = dt / 6.0;
+    const double sixth = DMAP ? a.sixth : dt / 6.0;
     const double half = dt / 2.0;
     const int32_t nsteps = (int32_t)a.nsteps;      // < 2^31 (mr_num_steps)
 
@@ -143,7 +149,7 @@ trace_kernel(const __grid_constant__ TraceArgs a)
                     // +0, which the strict path must not allow)
                     yt[0][c] = (MATH == MR_MATH_STRICT && st == 0) ? y[0][c] : adv;
                 }
-                rhs<BK, CK, MATH, UNI, 1>(a.b, a.c, yt, k);
+                rhs<BK, CK, MATH, UNI, 1, DMAP>(a.b, a.c, yt, k);
                 if (st == 0) k0_nan = all_nan4(k[0]);
 #pragma unroll
                 for (int c = 0; c < 4; ++c)
@@ -202,13 +208,20 @@ static cudaError_t launch_trace_math(const TraceArgs &args, cudaStream_t stream)
     TraceArgs a = args;
     a.off_y = (const char *)a.y - (const char *)a.x; a.off_kx = (const char *)a.kx - (const char *)a.x;
     a.off_ky = (const char *)a.ky - (const char *)a.x; a.row_bytes = a.ld * (int64_t)sizeof(double);
+    a.sixth = a.dt / 6.0;
     // the fast path's affine-coordinate specialisation needs every gridded field to qualify
     const bool uni = MATH == MR_MATH_FAST &&
                      (a.b.kind != MR_BATHY_GRID || a.b.uniform) && (a.c.kind != MR_CURRENT_GRID || a.c.uniform) &&
                      (a.b.kind == MR_BATHY_GRID || a.c.kind == MR_CURRENT_GRID);
     const unsigned grid = (unsigned)((a.n + (int64_t)kBlock - 1) / (int64_t)kBlock);
     constexpr bool kFast = MATH == MR_MATH_FAST;
-#define MR_LAUNCH(BKV, CKV, UNIV) trace_kernel<BKV, CKV, MATH, UNIV><<<grid, kBlock, 0, stream>>>(a)
+    // the depth-floor map needs the affine fast path on a gridded bathymetry that has one
+    const bool dmap = uni && a.deep_map && a.b.kind == MR_BATHY_GRID && a.b.dmap != nullptr;
+#define MR_LAUNCH(BKV, CKV, UNIV)                                                                              \
+    do {                                                                                                       \
+        if (dmap) trace_kernel<BKV, CKV, MATH, UNIV, kFast && UNIV && BKV == MR_BATHY_GRID><<<grid, kBlock, 0, stream>>>(a); \
+        else trace_kernel<BKV, CKV, MATH, UNIV, false><<<grid, kBlock, 0, stream>>>(a);                        \
+    } while (0)
 #define MR_CASE(BKV, CKV)                                                                                      \
     if (a.b.kind == BKV && a.c.kind == CKV) {                                                                  \
         if (uni) MR_LAUNCH(BKV, CKV, kFast);                                                                   \

@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def child(lib_path, rays, steps, workload, math, notraj=False, nx=2048):
+def child(lib_path, rays, steps, workload, math, notraj=False, nx=2048, flags=0):
     import numpy as np, torch
     from mantaray_b200 import _abi, _capi, workloads as W
     _capi.lib_path = lambda: lib_path
@@ -43,7 +43,7 @@ def child(lib_path, rays, steps, workload, math, notraj=False, nx=2048):
     d_rows = torch.empty(n, dtype=torch.int32, device=dev)
     d_len = torch.empty(n, dtype=torch.int32, device=dev)
     d_fin = torch.empty((4, n), dtype=torch.float64, device=dev)
-    opts = _abi.TraceOpts(wl.stride, math, 0, 0)
+    opts = _abi.TraceOpts(wl.stride, math, 0, flags)
     st = torch.cuda.current_stream()
     p = lambda t: C.c_void_p(t.data_ptr())
     tp = (lambda i: p(traj[i])) if traj is not None else (lambda i: None)
@@ -60,7 +60,7 @@ def child(lib_path, rays, steps, workload, math, notraj=False, nx=2048):
         best = min(best, e0.elapsed_time(e1))
     E = int((d_rows.to(torch.int64) - 1).sum().item())
     fin = d_fin.cpu().numpy()
-    print(json.dumps({"lib": os.path.basename(lib_path), "notraj": notraj, "nx": nx, "ms": best, "ray_steps_per_s": E / best * 1e3, "E": E,
+    print(json.dumps({"lib": os.path.basename(lib_path), "flags": flags, "workload": workload, "notraj": notraj, "nx": nx, "ms": best, "ray_steps_per_s": E / best * 1e3, "E": E,
                       "rows_sum": int(d_rows.sum().item()), "len_sum": int(d_len.sum().item()),
                       "fin_checksum": float(np.nansum(np.abs(fin[:2])) + 1e6 * np.nansum(np.abs(fin[2:])))}))
 
@@ -74,11 +74,12 @@ if __name__ == "__main__":
     ap.add_argument("--child", default=None)
     ap.add_argument("--notraj", action="store_true")
     ap.add_argument("--nx", type=int, default=2048)
+    ap.add_argument("--flags", type=int, default=0, help="mr_trace_opts.flags (1 = MR_OPT_DEEP_MAP)")
     ap.add_argument("libs", nargs="*")
     a = ap.parse_args()
     if a.child:
-        child(a.child, a.rays, a.steps, a.workload, a.math, a.notraj, a.nx)
+        child(a.child, a.rays, a.steps, a.workload, a.math, a.notraj, a.nx, a.flags)
     else:
         for lib in a.libs or [os.path.join(ROOT, "mantaray_b200", "libmantaray_b200.so")]:
             subprocess.run([sys.executable, __file__, "--child", os.path.abspath(lib), "--rays", str(a.rays),
-                            "--steps", str(a.steps), "--workload", a.workload, "--math", str(a.math), "--nx", str(a.nx)] + (["--notraj"] if a.notraj else []), check=False)
+                            "--steps", str(a.steps), "--workload", a.workload, "--math", str(a.math), "--nx", str(a.nx), "--flags", str(a.flags)] + (["--notraj"] if a.notraj else []), check=False)

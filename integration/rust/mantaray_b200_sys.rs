@@ -54,8 +54,10 @@ pub struct mr_trace_opts {
     pub stride: i32,
     pub math: i32,
     pub chunk_rays: i32,
-    pub reserved: i32,
+    pub flags: i32, // MR_OPT_* bits, 0 = defaults
 }
+
+pub const MR_OPT_DEEP_MAP: i32 = 1;
 
 #[repr(C)]
 pub struct mr_fields {

@@ -106,6 +106,7 @@ struct DeviceFields {
     int dev = -1;
     BathyDev b{};
     CurrentDev c{};
+    float deep_frac = 0.0f;    // share of the depth-floor map's blocks that are deep water for a 10 s wave
     std::vector<void *> allocs;
     WorkArea work;             // guarded by mr_fields::mu
 };
@@ -247,8 +248,11 @@ static bool affine_f32(const float *c, int n, float *d_out)
 // bilinear of interpolator.rs:59-83 returns, inside a cell, a value between its corners up to a few roundings of
 // terms no larger than ~2 zmax (< 1e-6 zmax), so every depth the lookup can produce in the block is >= H.
 // A block with a node that is NaN, infinite or <= 0 gets 0: no bound, the kernel looks the depth up.
-static std::vector<float> depth_floor_map(const double *depth, int nx, int ny, int *nbx_out, int *nby_out)
+// *deep_frac: the share of blocks with H >= 550 m (kh >= 22 for periods up to ~10 s), what an automatic choice
+// of MR_OPT_DEEP_MAP would look at.
+static std::vector<float> depth_floor_map(const double *depth, int nx, int ny, int *nbx_out, int *nby_out, float *deep_frac)
 {
+    size_t n_deep = 0;
     const int B = kDeepBlock;
     const int nbx = (nx - 1 + B - 1) / B, nby = (ny - 1 + B - 1) / B;
     std::vector<float> out((size_t)nbx * (size_t)nby, 0.0f);
@@ -271,9 +275,11 @@ static std::vector<float> depth_floor_map(const double *depth, int nx, int ny, i
             float v = sq >= (double)FLT_MAX ? FLT_MAX : (float)sq;
             if ((double)v > sq) v = std::nextafterf(v, 0.0f);
             out[(size_t)by * (size_t)nbx + (size_t)bx] = v;
+            n_deep += H >= 550.0;
         }
     }
     *nbx_out = nbx; *nby_out = nby;
+    *deep_frac = out.empty() ? 0.0f : (float)n_deep / (float)out.size();
     return out;
 }
 
@@ -350,7 +356,7 @@ static int upload_fields(DeviceFields &d, const mr_bathymetry_desc *b, const mr_
         B.dmap = nullptr; B.dmap_nbx = 0;
         if (B.uniform) {
             int nbx = 0, nby = 0;
-            std::vector<float> dm = depth_floor_map(b->depth, b->nx, b->ny, &nbx, &nby);
+            std::vector<float> dm = depth_floor_map(b->depth, b->nx, b->ny, &nbx, &nby, &d.deep_frac);
             if ((rc = upload(d, dm.data(), dm.size(), &B.dmap))) return rc;
             B.dmap_nbx = nbx;
         }
@@ -443,6 +449,15 @@ static void normalise_opts(const mr_trace_opts *in, mr_trace_opts &o)
     if (o.stride <= 0) o.stride = 1;
 }
 
+// MR_OPT_DEEP_MAP asks for the depth-floor map.  The automatic choice (a quarter of the blocks deep for a 10 s
+// wave: on shallower grids the map only adds a dependent load in front of every depth lookup) is written but
+// switched off until the flagged path has been through the parity suite on a GPU.
+static constexpr bool kDeepMapAuto = false;
+static int want_deep_map(const DeviceFields &d, const mr_trace_opts &o)
+{
+    return (o.flags & MR_OPT_DEEP_MAP) != 0 || (kDeepMapAuto && d.deep_frac >= 0.25f);
+}
+
 static int enqueue_trace(const DeviceFields &d, cudaStream_t stream, int64_t n,
                          const double *x0, const double *y0, const double *kx0, const double *ky0,
                          double dt, int64_t nsteps, const mr_trace_opts &o,
@@ -455,7 +470,7 @@ static int enqueue_trace(const DeviceFields &d, cudaStream_t stream, int64_t n,
     a.dt = dt; a.nsteps = nsteps; a.stride = o.stride;
     a.x = x; a.y = y; a.kx = kx; a.ky = ky; a.ld = ld;
     a.rows = rows; a.len = len; a.fin = fin;
-    a.deep_map = (o.flags & MR_OPT_DEEP_MAP) != 0;
+    a.deep_map = want_deep_map(d, o);
     cudaError_t e;
     if (o.math == MR_MATH_STRICT) e = launch_trace_strict(a, stream);
     else if (o.math == MR_MATH_FAST) e = launch_trace_fast(a, stream);
@@ -608,7 +623,7 @@ static int trace_block_on_device(DeviceFields &d, const HostJob &j, int64_t lo, 
                 a.x = tx; a.y = tx ? tx + plane : nullptr; a.kx = tx ? tx + 2 * plane : nullptr; a.ky = tx ? tx + 3 * plane : nullptr;
                 a.ld = chunk;
                 a.rows = B.rows; a.len = B.len; a.fin = B.fin;
-                a.deep_map = (j.o.flags & MR_OPT_DEEP_MAP) != 0;
+                a.deep_map = want_deep_map(d, j.o);
                 // fin is [4][n] with n = m for the kernel (it uses a.n as the pitch)
                 cudaError_t e = j.o.math == MR_MATH_STRICT ? launch_trace_strict(a, s_comp) : launch_trace_fast(a, s_comp);
                 if (e != cudaSuccess) { rc = bail(MR_ERR_CUDA, std::string("trace kernel launch: ") + cudaGetErrorString(e)); goto done; }

@@ -318,6 +318,15 @@ int  mr_measure_fp64_peak(int device, int millis, double *tflops);
  * spacing. */
 int  mr_selftest_fdiv(int device, float spacing, uint64_t *mismatches, int32_t *usable);
 
+/* The depth-floor map MR_OPT_DEEP_MAP consults, as the library builds it for a GRID bathymetry at upload:
+ * one float per block of 8 x 8 cells, row-major [*nby][*nbx], holding the square (rounded down) of a lower
+ * bound of every depth the reference's f32 bilinear lookup (src/bathymetry/cartesian_netcdf3.rs:98-135) can
+ * return inside the block, or 0 where there is no such bound (a NaN, infinite or non-positive node).
+ * `out` may be NULL to query the shape; `cap` is its capacity in floats.  *deep_frac (may be NULL): the share of
+ * blocks whose bound is at least 550 m.  Host only: works without a CUDA device. */
+int  mr_depth_floor_map(const mr_bathymetry_desc *bathy, float *out, size_t cap,
+                        int32_t *nbx, int32_t *nby, float *deep_frac);
+
 #ifdef __cplusplus
 }
 #endif

@@ -378,3 +378,15 @@ class ManyRays:
             m = int(res.rows[i])
             out.append((res.t[:m].copy(), np.stack([res.x[:m, i], res.y[:m, i], res.kx[:m, i], res.ky[:m, i]], axis=1)))
         return out
+
+
+def depth_floor_map(bathy):
+    """``mr_depth_floor_map``: ``(map[nby, nbx] f32, deep_frac)`` — per block of 8 x 8 cells the square of a lower
+    bound of every depth the lookup can return there (0: no bound).  Host only."""
+    lib = load()
+    bd = bathy.to_desc()
+    nbx, nby, frac = C.c_int32(), C.c_int32(), C.c_float()
+    _check(lib.mr_depth_floor_map(C.byref(bd), None, 0, C.byref(nbx), C.byref(nby), C.byref(frac)))
+    out = np.empty((nby.value, nbx.value), dtype=np.float32)
+    _check(lib.mr_depth_floor_map(C.byref(bd), out.ctypes.data, out.size, C.byref(nbx), C.byref(nby), C.byref(frac)))
+    return out, frac.value

@@ -1054,6 +1054,23 @@ int mr_measure_fp64_peak(int device, int millis, double *tflops)
     return MR_OK;
 }
 
+int mr_depth_floor_map(const mr_bathymetry_desc *b, float *out, size_t cap, int32_t *nbx, int32_t *nby, float *deep_frac)
+{
+    if (!b || !nbx || !nby) return fail(MR_ERR_BAD_ARG, "mr_depth_floor_map: NULL argument");
+    if (b->kind != MR_BATHY_GRID || b->nx < 2 || b->ny < 2 || !b->depth)
+        return fail(MR_ERR_BAD_ARG, "mr_depth_floor_map: needs a GRID bathymetry with nx, ny >= 2");
+    int bx = 0, by = 0;
+    float frac = 0.0f;
+    const std::vector<float> m = depth_floor_map(b->depth, b->nx, b->ny, &bx, &by, &frac);
+    *nbx = bx; *nby = by;
+    if (deep_frac) *deep_frac = frac;
+    if (out) {
+        if (cap < m.size()) return fail(MR_ERR_BAD_ARG, "mr_depth_floor_map: output too small");
+        std::memcpy(out, m.data(), m.size() * sizeof(float));
+    }
+    return MR_OK;
+}
+
 int mr_selftest_fdiv(int device, float spacing, uint64_t *mismatches, int32_t *usable)
 {
     if (!mismatches || !usable) return fail(MR_ERR_BAD_ARG, "mr_selftest_fdiv: NULL output");

@@ -120,3 +120,70 @@ def test_two_rank_sharding_over_gloo(tmp_path):
     line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
     r = json.loads(line)
     assert r["E"] == r["E_full"] and r["tmax"] == 2.0 and r["concat_ok"]
+
+
+# ---- the depth-floor map of MR_OPT_DEEP_MAP (host side; the kernel side is tests/test_gpu_deep_map.py) ----------
+def _map_cases():
+    from mantaray_b200 import CartesianNetcdf3
+    from test_gpu_fuzz import make_case
+
+    yield "C4", W.c4_agulhas(4, 4, 10, nx=256).bathymetry
+    yield "C2", W.c2_sea_mount(8, 10, half=200).bathymetry
+    yield "C5", W.c5_nazare(2, 2, 2, 10, nx=512).bathymetry
+    for seed in range(40):                              # even seeds: dry, infinite and NaN nodes
+        b = make_case(seed)[0]
+        if isinstance(b, CartesianNetcdf3):
+            yield f"fuzz{seed}", b
+
+
+def test_depth_floor_map_is_a_lower_bound_of_the_reference_lookup(oracle):
+    """Soundness of the shortcut: wherever the map holds H^2 > 0, every depth the reference's f32 bilinear
+    (oracle.sample_fields = BathymetryData::depth) returns in that block is >= H, on nodes, grid lines and
+    anywhere in between; blocks touching a NaN, infinite or non-positive node hold 0.  And the kernel's f32 test
+    RN(f32(k^2) * H^2) >= 484.01 then implies k * depth >= 22 for the depth the lookup would have returned."""
+    from mantaray_b200 import ConstantCurrent
+    from mantaray_b200._capi import depth_floor_map
+
+    rng = np.random.default_rng(11)
+    checked = 0
+    for name, b in _map_cases():
+        m, frac = depth_floor_map(b)
+        nx, ny = b.x.size, b.y.size
+        assert m.shape == ((ny - 1 + 7) // 8, (nx - 1 + 7) // 8), name
+        assert 0.0 <= frac <= 1.0
+        x, y = b.x.astype(np.float64), b.y.astype(np.float64)
+        if not (np.all(np.diff(x) > 0) and np.all(np.diff(y) > 0)):
+            continue                                    # (a descending axis: the affine fast path is not used there)
+        z32 = np.asarray(b.depth, dtype=np.float64).reshape(ny, nx).astype(np.float32)
+        # blocks with a bad node hold 0
+        for by in range(m.shape[0]):
+            for bx in range(m.shape[1]):
+                blk = z32[by * 8: min(by * 8 + 8, ny - 1) + 1, bx * 8: min(bx * 8 + 8, nx - 1) + 1]
+                if not (np.isfinite(blk).all() and (blk > 0).all()):
+                    assert m[by, bx] == 0.0, f"{name}: block ({by},{bx}) has a bad node but a bound"
+        # random points, points on grid lines and nodes
+        n = 60_000
+        px = rng.uniform(x[0], x[-1], n)
+        py = rng.uniform(y[0], y[-1], n)
+        px[: n // 8] = rng.choice(x, n // 8)
+        py[n // 16: n // 5] = rng.choice(y, n // 5 - n // 16)
+        depth, _, _ = oracle.sample_fields(b, ConstantCurrent(0.0, 0.0), px, py)
+        # the cell the reference picks (cartesian_netcdf3.rs:274-296, 334-390): f32 index, floor, clamped to n-2
+        fx = (px.astype(np.float32) - b.x[0]) / np.abs(b.x[1] - b.x[0])
+        fy = (py.astype(np.float32) - b.y[0]) / np.abs(b.y[1] - b.y[0])
+        inside = (fx >= 0) & (fx <= np.float32(nx - 1)) & (fy >= 0) & (fy <= np.float32(ny - 1))
+        cx = np.clip(np.floor(fx).astype(np.int64), 0, nx - 2)
+        cy = np.clip(np.floor(fy).astype(np.int64), 0, ny - 2)
+        hsq = m[cy >> 3, cx >> 3]
+        sel = inside & (hsq > 0)
+        H = np.sqrt(hsq[sel].astype(np.float64))
+        d = depth[sel].astype(np.float64)
+        assert not np.isnan(d).any(), f"{name}: a bounded block produced a failed lookup"
+        assert (d >= H).all(), f"{name}: lookup below the block's bound by {np.max(H - d)}"
+        # the kernel's test in its own arithmetic
+        k = 10.0 ** rng.uniform(-3, 1, sel.sum())
+        k2f = (k * k).astype(np.float32)
+        deep = (k2f * hsq[sel]).astype(np.float32) >= np.float32(484.01)
+        assert (k[deep] * d[deep] >= 22.0).all(), f"{name}: flagged deep with kh = {np.min(k[deep] * d[deep])}"
+        checked += int(deep.sum())
+    assert checked > 50_000

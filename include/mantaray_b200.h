@@ -323,9 +323,12 @@ int  mr_selftest_fdiv(int device, float spacing, uint64_t *mismatches, int32_t *
  * bound of every depth the reference's f32 bilinear lookup (src/bathymetry/cartesian_netcdf3.rs:98-135) can
  * return inside the block, or 0 where there is no such bound (a NaN, infinite or non-positive node).
  * `out` may be NULL to query the shape; `cap` is its capacity in floats.  *deep_frac (may be NULL): the share of
- * blocks whose bound is at least 550 m.  Host only: works without a CUDA device. */
+ * blocks whose bound is at least 550 m.  *affine (may be NULL): 1 if the grid's f32 coordinates are exactly affine,
+ * which is when the fast path uses launch-constant cell geometry and the map at all (on other grids the reference's
+ * lookup may extrapolate beyond a cell's corners, and the bound does not hold).  Host only: works without a
+ * CUDA device. */
 int  mr_depth_floor_map(const mr_bathymetry_desc *bathy, float *out, size_t cap,
-                        int32_t *nbx, int32_t *nby, float *deep_frac);
+                        int32_t *nbx, int32_t *nby, float *deep_frac, int32_t *affine);
 
 #ifdef __cplusplus
 }

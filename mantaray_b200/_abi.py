@@ -157,7 +157,7 @@ SIGNATURES = {
     "mr_measure_fp64_peak": (C.c_int, [C.c_int, C.c_int, c_double_p]),
     "mr_selftest_fdiv": (C.c_int, [C.c_int, C.c_float, C.POINTER(C.c_uint64), c_int32_p]),
     "mr_depth_floor_map": (C.c_int, [C.POINTER(BathymetryDesc), C.c_void_p, C.c_size_t, c_int32_p, c_int32_p,
-                                     C.POINTER(C.c_float)]),
+                                     C.POINTER(C.c_float), c_int32_p]),
 }
 
 

@@ -381,12 +381,14 @@ class ManyRays:
 
 
 def depth_floor_map(bathy):
-    """``mr_depth_floor_map``: ``(map[nby, nbx] f32, deep_frac)`` — per block of 8 x 8 cells the square of a lower
-    bound of every depth the lookup can return there (0: no bound).  Host only."""
+    """``mr_depth_floor_map``: ``(map[nby, nbx] f32, deep_frac, affine)`` — per block of 8 x 8 cells the square of a
+    lower bound of every depth the lookup can return there (0: no bound); ``affine`` tells whether the fast path
+    would use it on this grid.  Host only."""
     lib = load()
     bd = bathy.to_desc()
-    nbx, nby, frac = C.c_int32(), C.c_int32(), C.c_float()
-    _check(lib.mr_depth_floor_map(C.byref(bd), None, 0, C.byref(nbx), C.byref(nby), C.byref(frac)))
+    nbx, nby, frac, aff = C.c_int32(), C.c_int32(), C.c_float(), C.c_int32()
+    _check(lib.mr_depth_floor_map(C.byref(bd), None, 0, C.byref(nbx), C.byref(nby), C.byref(frac), C.byref(aff)))
     out = np.empty((nby.value, nbx.value), dtype=np.float32)
-    _check(lib.mr_depth_floor_map(C.byref(bd), out.ctypes.data, out.size, C.byref(nbx), C.byref(nby), C.byref(frac)))
-    return out, frac.value
+    _check(lib.mr_depth_floor_map(C.byref(bd), out.ctypes.data, out.size, C.byref(nbx), C.byref(nby), C.byref(frac),
+                                  C.byref(aff)))
+    return out, frac.value, bool(aff.value)

@@ -1054,11 +1054,17 @@ int mr_measure_fp64_peak(int device, int millis, double *tflops)
     return MR_OK;
 }
 
-int mr_depth_floor_map(const mr_bathymetry_desc *b, float *out, size_t cap, int32_t *nbx, int32_t *nby, float *deep_frac)
+int mr_depth_floor_map(const mr_bathymetry_desc *b, float *out, size_t cap, int32_t *nbx, int32_t *nby, float *deep_frac,
+                       int32_t *affine)
 {
     if (!b || !nbx || !nby) return fail(MR_ERR_BAD_ARG, "mr_depth_floor_map: NULL argument");
-    if (b->kind != MR_BATHY_GRID || b->nx < 2 || b->ny < 2 || !b->depth)
+    if (b->kind != MR_BATHY_GRID || b->nx < 2 || b->ny < 2 || !b->depth || !b->x || !b->y)
         return fail(MR_ERR_BAD_ARG, "mr_depth_floor_map: needs a GRID bathymetry with nx, ny >= 2");
+    if (affine) {       // the same test upload_fields applies before it builds (and the kernel consults) the map
+        float rsx, rsy, dxf, dyf, c01, c10;
+        *affine = recip_ok(fabsf(b->x[1] - b->x[0]), &rsx) && recip_ok(fabsf(b->y[1] - b->y[0]), &rsy) &&
+                  affine_f32(b->x, b->nx, &dxf) && affine_f32(b->y, b->ny, &dyf) && basis_coeffs(dxf, dyf, &c01, &c10);
+    }
     int bx = 0, by = 0;
     float frac = 0.0f;
     const std::vector<float> m = depth_floor_map(b->depth, b->nx, b->ny, &bx, &by, &frac);

@@ -68,6 +68,8 @@ def parse():
     ap.add_argument("--workload", default="C4", choices=["C1", "C2", "C3", "C4", "C5"])
     ap.add_argument("--rays-per-gpu", type=int, default=0, help="override the per-GPU batch (testing)")
     ap.add_argument("--math", default="fast", choices=["fast", "strict"])
+    ap.add_argument("--deep-map", default="auto", choices=["auto", "on", "off"],
+                    help="depth-floor map of the fast path (mr_trace_opts.flags): the library's own choice, forced on, forced off")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
@@ -233,7 +235,7 @@ def main():
     import torch
     import torch.distributed as dist
 
-    from mantaray_b200 import _abi, _capi
+    from mantaray_b200 import CartesianNetcdf3, _abi, _capi
     from mantaray_b200 import workloads as W
 
     rank = int(os.environ.get("RANK", "0"))
@@ -284,7 +286,14 @@ def main():
     d_rows = torch.empty(n, dtype=torch.int32, device=dev)
     d_len = torch.empty(n, dtype=torch.int32, device=dev)
     d_fin = torch.empty((4, n), dtype=torch.float64, device=dev)
-    opts = _abi.TraceOpts(wl.stride, math_mode, 0, 0)
+    flags = {"auto": 0, "on": _abi.MR_OPT_DEEP_MAP, "off": _abi.MR_OPT_NO_DEEP_MAP}[args.deep_map]
+    opts = _abi.TraceOpts(wl.stride, math_mode, 0, flags)
+    # what the library does with those flags on this grid (include/mantaray_b200.h): the map exists on affine
+    # gridded bathymetry, and the default uses it when a quarter of its blocks are deep for a 10 s wave
+    deep_map_used, deep_share = False, None
+    if args.math == "fast" and isinstance(wl.bathymetry, CartesianNetcdf3):
+        _, deep_share, affine = _capi.depth_floor_map(wl.bathymetry)
+        deep_map_used = bool(affine) and args.deep_map != "off" and (args.deep_map == "on" or deep_share >= 0.25)
     stream = torch.cuda.current_stream()
     launches = C.c_int32(0)
 
@@ -356,6 +365,8 @@ def main():
         "bound": "fp64", "kernel": "mr::trace_kernel<GRID,GRID,%s>" % args.math,
         "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_tf / fp64_peak if fp64_peak else None,
         "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read+write); algorithmic bytes per launch = %d" % int(alg_bytes),
+        "traffic_note": ("captured on the kernel without the depth-floor map (profiles/r1/m_*); with the map the writes are "
+                         "the same and the record reads can only be fewer") if (traffic and deep_map_used) else None,
         "flop_per_ray_step": wl.flop_per_ray_step,
         "peak_source": "DFMA probe kernel timed in this run (mr_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
         "kernel_ms": kernel_ms,
@@ -432,6 +443,7 @@ def main():
                 "workload": wl.name, "description": wl.description, "rays": wl.n_rays, "rays_per_gpu": n,
                 "rk4_steps": wl.n_steps, "grid": [int(wl.bathymetry.x.size), int(wl.bathymetry.y.size)],
                 "stride": wl.stride, "output": wl.output, "math": args.math,
+                "deep_map": {"flag": args.deep_map, "used": deep_map_used, "deep_share_of_blocks": deep_share},
                 "executed_ray_steps_per_pass": E, "parallelism": f"rays sharded x{world}, fields replicated, no collective",
                 "l2": "no flush needed: each pass writes %.1f GB of trajectories per GPU, far larger than the 126 MB L2" % (
                     rows_cap * n * 32 / 1e9) if full else "final-state only: inputs (fields %.0f MB) re-read each pass" % (

@@ -122,11 +122,16 @@ typedef struct mr_trace_opts {
     int32_t flags;        /* MR_OPT_* bits; 0 = defaults                                              */
 } mr_trace_opts;
 
-/* MR_MATH_FAST on affine gridded bathymetry: skip the depth lookup wherever a per-block lower bound of
- * the depth already proves kh >= 22, where the reference's own formulas no longer depend on h (see
- * DESIGN.md).  Same rows / len; values equal to the unflagged fast path up to the sign of an exact zero.
- * Off by default in this round (measured, not yet run through the whole parity suite). */
-#define MR_OPT_DEEP_MAP 1
+/* Depth-floor map.  MR_MATH_FAST on affine gridded bathymetry skips the depth lookup wherever a per-block
+ * lower bound of the depth already proves kh >= 22, where the reference's own formulas no longer depend on
+ * h.  Same rows / len; values equal to the path without the map up to the sign of an
+ * exact zero.  By default (flags = 0) the library uses the map when at least a quarter of the grid's blocks
+ * are deep for a 10 s wave (mr_depth_floor_map's *deep_frac >= 0.25); on shallower grids it only adds a
+ * dependent load in front of every depth lookup.
+ *   MR_OPT_DEEP_MAP    : use the map whenever the grid has one, whatever its deep share
+ *   MR_OPT_NO_DEEP_MAP : never use it (wins over MR_OPT_DEEP_MAP)                                     */
+#define MR_OPT_DEEP_MAP    1
+#define MR_OPT_NO_DEEP_MAP 2
 
 /* ---- library ------------------------------------------------------------- */
 

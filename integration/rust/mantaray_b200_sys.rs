@@ -58,6 +58,7 @@ pub struct mr_trace_opts {
 }
 
 pub const MR_OPT_DEEP_MAP: i32 = 1;
+pub const MR_OPT_NO_DEEP_MAP: i32 = 2;
 
 #[repr(C)]
 pub struct mr_fields {

@@ -71,6 +71,7 @@ class CurrentDesc(C.Structure):
 
 
 MR_OPT_DEEP_MAP = 1
+MR_OPT_NO_DEEP_MAP = 2
 
 
 class TraceOpts(C.Structure):

@@ -449,13 +449,14 @@ static void normalise_opts(const mr_trace_opts *in, mr_trace_opts &o)
     if (o.stride <= 0) o.stride = 1;
 }
 
-// MR_OPT_DEEP_MAP asks for the depth-floor map.  The automatic choice (a quarter of the blocks deep for a 10 s
-// wave: on shallower grids the map only adds a dependent load in front of every depth lookup) is written but
-// switched off until the flagged path has been through the parity suite on a GPU.
-static constexpr bool kDeepMapAuto = false;
+// The depth-floor map.  Automatic choice: a quarter of the blocks deep for a 10 s wave — on
+// shallower grids the map only adds a dependent load in front of every depth lookup.  MR_OPT_DEEP_MAP forces
+// it on for any grid that has one, MR_OPT_NO_DEEP_MAP off.
+static constexpr float kDeepMapAutoShare = 0.25f;
 static int want_deep_map(const DeviceFields &d, const mr_trace_opts &o)
 {
-    return (o.flags & MR_OPT_DEEP_MAP) != 0 || (kDeepMapAuto && d.deep_frac >= 0.25f);
+    if (o.flags & MR_OPT_NO_DEEP_MAP) return 0;
+    return (o.flags & MR_OPT_DEEP_MAP) != 0 || d.deep_frac >= kDeepMapAutoShare;
 }
 
 static int enqueue_trace(const DeviceFields &d, cudaStream_t stream, int64_t n,

@@ -1,8 +1,8 @@
-"""MR_OPT_DEEP_MAP (include/mantaray_b200.h): the fast path skips the depth lookup wherever a per-block lower
-bound of the depth proves kh >= 22.  The flag is OFF by default this round — it was measured (C4: 63.8 -> 56.9 ms
-per 1M-ray launch, identical rows / len / final-state checksums) after the round's GPU time for the full parity
-suite had run out — and so are these tests: run them with MR_TEST_DEEP_MAP=1.  They hold the flagged path to
-the oracle (same bar as everywhere) and to the unflagged path (identical up to the sign of an exact zero)."""
+"""The depth-floor map (include/mantaray_b200.h): the fast path skips the depth lookup wherever a
+per-block lower bound of the depth proves kh >= 22.  It is on by default where a quarter of the grid's blocks are
+deep for a 10 s wave; MR_OPT_DEEP_MAP forces it on, MR_OPT_NO_DEEP_MAP off.  These tests hold the path WITH the
+map to the oracle (same bar as everywhere) and to the path WITHOUT it (identical up to the sign of an exact zero),
+on every grid that has a map, whatever its deep share."""
 
 import os
 
@@ -12,16 +12,14 @@ import pytest
 from conftest import assert_parity
 from mantaray_b200 import MR_MATH_FAST, CartesianCurrent, CartesianNetcdf3, ConstantCurrent, Fields, trace_many
 from mantaray_b200 import workloads as W
-from mantaray_b200._abi import MR_OPT_DEEP_MAP
+from mantaray_b200._abi import MR_OPT_DEEP_MAP, MR_OPT_NO_DEEP_MAP
 from test_gpu_fuzz import make_case
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("MR_TEST_DEEP_MAP") != "1",
-                                 reason="opt-in: MR_OPT_DEEP_MAP is not enabled by default this round (MR_TEST_DEEP_MAP=1)")]
+pytestmark = pytest.mark.gpu
 
 
 def both(f, rays, t_end, dt, **kw):
-    plain = trace_many(f, *rays, 0.0, t_end, dt, math=MR_MATH_FAST, final_state=True, **kw)
+    plain = trace_many(f, *rays, 0.0, t_end, dt, math=MR_MATH_FAST, final_state=True, flags=MR_OPT_NO_DEEP_MAP, **kw)
     mapped = trace_many(f, *rays, 0.0, t_end, dt, math=MR_MATH_FAST, final_state=True, flags=MR_OPT_DEEP_MAP, **kw)
     return plain, mapped
 
@@ -91,3 +89,21 @@ def test_blocks_with_dry_and_non_finite_nodes_fall_back_to_the_lookup(oracle, gp
             plain, mapped = both(f, (x0, y0, kx0, ky0), dt * steps, dt)
         assert_parity(mapped, ref, what="dry / non-finite blocks with the depth-floor map")
         assert_same(mapped, plain, "dry / non-finite blocks")
+
+
+def test_default_follows_the_deep_share_of_the_grid(gpu):
+    """flags = 0: the map is used on C4's deep basin (share >= 1/4) and not on C5's 400 m shelf; either way the
+    rows are those of both forced variants, and MR_OPT_NO_DEEP_MAP wins over MR_OPT_DEEP_MAP."""
+    from mantaray_b200 import depth_floor_map
+    for wl, deep in ((W.c4_agulhas(16, 16, 300, nx=256), True), (W.c5_nazare(4, 4, 16, 600, nx=512), False)):
+        _, share, affine = depth_floor_map(wl.bathymetry)
+        assert affine and (share >= 0.25) == deep
+        rays = wl.all_rays()
+        with Fields(wl.bathymetry, wl.current, devices=[0]) as f:
+            plain, mapped = both(f, rays, wl.duration, wl.dt, stride=wl.stride)
+            auto = trace_many(f, *rays, 0.0, wl.duration, wl.dt, final_state=True, stride=wl.stride)
+            off = trace_many(f, *rays, 0.0, wl.duration, wl.dt, final_state=True, stride=wl.stride,
+                             flags=MR_OPT_DEEP_MAP | MR_OPT_NO_DEEP_MAP)
+        assert_same(auto, mapped if deep else plain, "default flags")
+        assert_same(off, plain, "both flags")
+        assert_same(mapped, plain, "forced")

@@ -221,7 +221,7 @@ def run_reference(args):
                    "grid": [wl.bathymetry.x.size, wl.bathymetry.y.size], "stride": wl.stride},
         "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "gpu_launches": 0, "warmup_passes_run": min(args.warmup, 1),   # a CPU pass takes ~10 s: at most one is spent untimed
     }
     emit(line)
 

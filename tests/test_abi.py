@@ -77,3 +77,42 @@ def test_descriptor_validation_messages():
     assert lib.mr_fields_create(C.byref(b), C.byref(c), 1, C.byref(h)) == _abi.MR_ERR_BAD_ARG
     assert lib.mr_fields_create(None, C.byref(c), 1, C.byref(h)) == _abi.MR_ERR_BAD_ARG
     assert lib.mr_trace_many(None, 1, None, None, None, None, 0.0, 1.0, 1.0, None, *([None] * 8)) == _abi.MR_ERR_BAD_ARG
+
+
+def _build_cpp_example(tmp_path):
+    """integration/cpp/example.cpp: the C++ host mirror of ManyRays (src/ray.rs:24-127) over the C ABI."""
+    import shutil
+    import subprocess
+
+    cxx = shutil.which("g++")
+    if cxx is None:
+        pytest.skip("no g++ on this box")
+    exe = str(tmp_path / "example")
+    libdir = os.path.dirname(_capi.lib_path())
+    subprocess.run([cxx, "-std=c++17", "-Wall", "-Wextra", "-Werror", os.path.join(ROOT, "integration", "cpp", "example.cpp"),
+                    "-L" + libdir, "-lmantaray_b200", "-Wl,-rpath," + libdir, "-o", exe], check=True)
+    return subprocess.run([exe], capture_output=True, text=True, timeout=120)
+
+
+@pytest.mark.skipif(_capi.device_count() > 0, reason="needs a box WITHOUT a GPU")
+def test_cpp_host_mirror_compiles_and_fails_loudly_without_gpu(tmp_path):
+    r = _build_cpp_example(tmp_path)
+    assert r.returncode == 0 and "error %d" % _abi.MR_ERR_CUDA in r.stdout and "no CPU fallback" in r.stdout
+
+
+@pytest.mark.gpu
+def test_cpp_host_mirror_runs_the_beach(tmp_path, oracle):
+    """The same two rays through the Python mirror's oracle back-end: row counts and the last finite x agree."""
+    from mantaray_b200 import ConstantSlope
+
+    r = _build_cpp_example(tmp_path)
+    assert r.returncode == 0, r.stdout + r.stderr
+    got = re.findall(r"(\d+) rows, last finite x = ([-0-9.]+)", r.stdout)
+    assert len(got) == 2, r.stdout
+    k = 0.05
+    ref = oracle.trace_many(ConstantSlope(100.0, 0.0, 0.0, -0.05, 0.0), ConstantCurrent(0.0, 0.0),
+                            np.zeros(2), np.zeros(2), np.array([k * np.cos(np.pi / 6), k]), np.array([k * np.sin(np.pi / 6), 0.0]),
+                            0.0, 1000.0, 1.0)
+    for i, (rows, x_last) in enumerate(got):
+        assert int(rows) == ref.rows[i]
+        assert abs(float(x_last) - ref.x[ref.rows[i] - 2, i]) <= 1e-3

@@ -171,13 +171,18 @@ def cpu_leg(wl, seconds_per_step: float = 12.0, steps: int = 1, warmup: int = 0)
 
     O.build()
     cores = os.cpu_count() or 1
-    # calibrate: ~0.45e6 ray-steps/s per thread on this class of CPU
-    probe = strided_sample(wl, 4 * cores)
-    t = time.perf_counter()
-    r = O.trace_many(wl.bathymetry, wl.current, *probe, wl.t0, wl.duration, wl.dt, stride=wl.stride,
-                     nthreads=cores, trajectories=False, final_state=False)
-    dtp = time.perf_counter() - t
-    rate = max(float((r.rows - 1).sum()) / max(dtp, 1e-6), 1.0)
+    # calibrate: the probe runs twice and the second pass counts (the first pass over a set of rays pays ~1 s of
+    # cold misses on the field arrays); it is large enough (~0.1 s or more) that thread start-up does not dominate
+    def probe_pass(n_probe):
+        rays_p = strided_sample(wl, n_probe)
+        t = time.perf_counter()
+        r = O.trace_many(wl.bathymetry, wl.current, *rays_p, wl.t0, wl.duration, wl.dt, stride=wl.stride,
+                         nthreads=cores, trajectories=False, final_state=False)
+        return time.perf_counter() - t, float((r.rows - 1).sum())
+
+    probe_pass(64 * cores)
+    t_probe, e_probe = probe_pass(64 * cores)
+    rate = max(e_probe / max(t_probe, 1e-6), 1.0)
     n_sample = int(min(wl.n_rays, max(8 * cores, rate * seconds_per_step / max(wl.n_steps, 1))))
     rays = strided_sample(wl, n_sample)
     n_sample = rays[0].size

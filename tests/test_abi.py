@@ -116,3 +116,33 @@ def test_cpp_host_mirror_runs_the_beach(tmp_path, oracle):
     for i, (rows, x_last) in enumerate(got):
         assert int(rows) == ref.rows[i]
         assert abs(float(x_last) - ref.x[ref.rows[i] - 2, i]) <= 1e-3
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    """No silent fallback: without the built CUDA extension every entry into the product raises ImportError."""
+    import mantaray_b200
+
+    monkeypatch.setattr(_capi, "_lib", None)
+    monkeypatch.setattr(_capi, "lib_path", lambda: os.path.join(ROOT, "mantaray_b200", "no_such_library.so"))
+    with pytest.raises(ImportError, match="no CPU fallback"):
+        _capi.load()
+    with pytest.raises(ImportError):
+        mantaray_b200.ray_tracing([0.0], [0.0], [0.1], [0.0], 10.0, 1.0, "bathy.nc", "current.nc")
+    with pytest.raises(ImportError):
+        _capi.Fields(ConstantDepth(10.0), ConstantCurrent(0, 0))
+
+
+def test_product_never_touches_the_oracle():
+    """oracle/ is test infrastructure: nothing under mantaray_b200/ (Python or C++/CUDA) or include/ refers to it."""
+    offenders = []
+    for base in ("mantaray_b200", "mantaray", "include", "integration"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, base)):
+            if "build" in os.path.basename(dirpath):
+                continue
+            for name in files:
+                if not name.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h", ".rs", "Makefile")):
+                    continue
+                text = open(os.path.join(dirpath, name), errors="replace").read()
+                if re.search(r"libmr_oracle|\bfrom oracle\b|\bimport oracle\b|\borc_[a-z_]+\s*\(|mr_oracle\.h", text):
+                    offenders.append(os.path.relpath(os.path.join(dirpath, name), ROOT))
+    assert offenders == []

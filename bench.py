@@ -367,7 +367,7 @@ def main():
     except Exception:
         pass
     roofline = {
-        "bound": "fp64", "kernel": "mr::trace_kernel<GRID,GRID,%s>" % args.math,
+        "bound": "fp64", "kernel": "mr::trace_kernel<GRID,GRID,%s%s>" % (args.math, ",depth-floor map" if deep_map_used else ""),
         "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_tf / fp64_peak if fp64_peak else None,
         "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read+write); algorithmic bytes per launch = %d" % int(alg_bytes),
         "traffic_note": ("captured on the kernel without the depth-floor map (profiles/r1/m_*); with the map the writes are "

@@ -146,3 +146,22 @@ def test_product_never_touches_the_oracle():
                 if re.search(r"libmr_oracle|\bfrom oracle\b|\bimport oracle\b|\borc_[a-z_]+\s*\(|mr_oracle\.h", text):
                     offenders.append(os.path.relpath(os.path.join(dirpath, name), ROOT))
     assert offenders == []
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/mantaray_b200.h is the boundary a cgo / Rust-bindgen / ctypes user binds: it has to be C, not C++."""
+    import shutil
+    import subprocess
+
+    cc = shutil.which("gcc")
+    if cc is None:
+        pytest.skip("no gcc on this box")
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "mantaray_b200.h"\n'
+                   "int main(void) { mr_trace_opts o = {1, MR_MATH_FAST, 0, MR_OPT_NO_DEEP_MAP}; (void)o;\n"
+                   "                 return mr_abi_version() == 1 && mr_num_rows(0.0, 10.0, 2.0, 1) == 6 ? 0 : 1; }\n")
+    libdir = os.path.dirname(_capi.lib_path())
+    exe = str(tmp_path / "hdr")
+    subprocess.run([cc, "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(ROOT, "include"), str(src),
+                    "-L" + libdir, "-lmantaray_b200", "-Wl,-rpath," + libdir, "-o", exe], check=True)
+    assert subprocess.run([exe]).returncode == 0

@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def child(lib_path, rays, steps, workload, math, notraj=False, nx=2048, flags=0):
+def child(lib_path, rays, steps, workload, math, notraj=False, nx=2048, flags=0, order="start"):
     import numpy as np, torch
     from mantaray_b200 import _abi, _capi, workloads as W
     _capi.lib_path = lambda: lib_path
@@ -22,6 +22,22 @@ def child(lib_path, rays, steps, workload, math, notraj=False, nx=2048, flags=0)
           "C3": lambda: W.c3_shear_jet(rays, steps), "C5": lambda: W.c5_nazare(8, 8, rays // 64, steps)}[workload]()
     x0, y0, kx0, ky0 = wl.all_rays()
     n = x0.size
+    if order != "start":
+        # The same rays in another order (C4: ray = start point * side + direction).  Which rays share a warp, a
+        # block and a wave of resident blocks decides how often a cell record is fetched again;
+        # rows_sum / len_sum / fin_checksum are sums over rays and must not move.
+        assert workload == "C4", "--order is defined for C4's (start point, direction) lattice"
+        s_, d_ = np.divmod(np.arange(n), side)
+        if order == "dir":                       # direction-major: a warp is 32 neighbouring start points, one direction
+            key = d_ * side + s_
+        elif order == "tile":                    # a block is 128 neighbouring directions of one start point, blocks run
+            key = ((d_ // 128) * side + s_) * 128 + d_ % 128       # across all start points before the next 128 directions
+        elif order == "tile32":                  # the same with warp-sized direction groups
+            key = ((d_ // 32) * side + s_) * 32 + d_ % 32
+        else:
+            raise SystemExit(f"unknown --order {order}")
+        perm = np.argsort(key, kind="stable")
+        x0, y0, kx0, ky0 = x0[perm], y0[perm], kx0[perm], ky0[perm]
     if os.environ.get("KB_ANALYTIC"):      # same rays, analytic fields: no record loads at all
         from mantaray_b200 import ConstantDepth, ConstantCurrent, ConstantSlope
         mode = os.environ["KB_ANALYTIC"]
@@ -60,7 +76,7 @@ def child(lib_path, rays, steps, workload, math, notraj=False, nx=2048, flags=0)
         best = min(best, e0.elapsed_time(e1))
     E = int((d_rows.to(torch.int64) - 1).sum().item())
     fin = d_fin.cpu().numpy()
-    print(json.dumps({"lib": os.path.basename(lib_path), "flags": flags, "workload": workload, "notraj": notraj, "nx": nx, "ms": best, "ray_steps_per_s": E / best * 1e3, "E": E,
+    print(json.dumps({"lib": os.path.basename(lib_path), "flags": flags, "order": order, "workload": workload, "notraj": notraj, "nx": nx, "ms": best, "ray_steps_per_s": E / best * 1e3, "E": E,
                       "rows_sum": int(d_rows.sum().item()), "len_sum": int(d_len.sum().item()),
                       "fin_checksum": float(np.nansum(np.abs(fin[:2])) + 1e6 * np.nansum(np.abs(fin[2:])))}))
 
@@ -75,11 +91,13 @@ if __name__ == "__main__":
     ap.add_argument("--notraj", action="store_true")
     ap.add_argument("--nx", type=int, default=2048)
     ap.add_argument("--flags", type=int, default=0, help="mr_trace_opts.flags (0 = library default, 1 = MR_OPT_DEEP_MAP, 2 = MR_OPT_NO_DEEP_MAP)")
+    ap.add_argument("--order", default="start", choices=["start", "dir", "tile", "tile32"],
+                    help="C4 only: order of the same rays (start-point-major as benchmarked, direction-major, or tiled)")
     ap.add_argument("libs", nargs="*")
     a = ap.parse_args()
     if a.child:
-        child(a.child, a.rays, a.steps, a.workload, a.math, a.notraj, a.nx, a.flags)
+        child(a.child, a.rays, a.steps, a.workload, a.math, a.notraj, a.nx, a.flags, a.order)
     else:
         for lib in a.libs or [os.path.join(ROOT, "mantaray_b200", "libmantaray_b200.so")]:
             subprocess.run([sys.executable, __file__, "--child", os.path.abspath(lib), "--rays", str(a.rays),
-                            "--steps", str(a.steps), "--workload", a.workload, "--math", str(a.math), "--nx", str(a.nx), "--flags", str(a.flags)] + (["--notraj"] if a.notraj else []), check=False)
+                            "--steps", str(a.steps), "--workload", a.workload, "--math", str(a.math), "--nx", str(a.nx), "--flags", str(a.flags), "--order", a.order] + (["--notraj"] if a.notraj else []), check=False)

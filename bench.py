@@ -2,15 +2,21 @@
 """bench.py — ray-steps/s of the batch ray-tracing hot path on B200.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload C4]
+                    [--shard block|interleave] [--no-extra] [--inproc]
 
 One "step" is one pass of the hot path over one batch: every ray of the workload
 integrated for all its RK4 steps (one kernel launch).  The default workload is
 C4 (BASELINE.json configs[3]: Agulhas-like eddy current + variable bathymetry on a
 2048x2048 f64 grid, 1M rays, 2048 RK4 steps, full trajectory output) — the
 "1M-ray current+bathymetry config" the north_star quotes its target on; it fits
-one GPU (65.6 GB of trajectories).  With N GPUs every rank traces its own
-contiguous block of 1M rays of an N-times denser ensemble (weak scaling; rays are
-independent, so there is no data-path collective).
+one GPU (65.6 GB of trajectories).  With N GPUs every rank traces its own share
+of an N-times larger ensemble (weak scaling; rays are independent, so there is
+no data-path collective).
+
+After the headline workload the other named shapes (C1, C2, C3 and the C5 shard)
+run at their BASELINE.json sizes, a few passes each, and are reported in
+"workloads"; every workload's TIMED output buffers are then checked against the
+CPU oracle on a strided sample of rays ("parity").
 
 Printed by rank 0: ONE JSON line (see README / DESIGN.md for the keys).
 """
@@ -34,6 +40,8 @@ sys.path.insert(0, ROOT)
 
 METRIC = "fp64_ray_steps_per_sec"
 UNIT = "ray-steps/s"
+PARITY_TOL = 1e-9                  # BASELINE.json north_star: relative error in position and wavenumber
+FP64_FLOP_PER_CLK_PER_SM = 128     # 64 DFMA lanes x 2 flop
 
 
 # The contract is ONE JSON line on stdout.  Libraries print there too (NCCL announces its version on the
@@ -70,8 +78,19 @@ def parse():
     ap.add_argument("--math", default="fast", choices=["fast", "strict"])
     ap.add_argument("--deep-map", default="auto", choices=["auto", "on", "off"],
                     help="depth-floor map of the fast path (mr_trace_opts.flags): the library's own choice, forced on, forced off")
+    ap.add_argument("--same-grid", default="auto", choices=["auto", "off"],
+                    help="same-grid shortcut of the fast path: the library's own choice, or MR_OPT_NO_SAME_GRID")
+    ap.add_argument("--shard", default="auto", choices=["auto", "block", "interleave"],
+                    help="how the ensemble is shared out over the ranks: one contiguous block each, or tiles dealt round-robin "
+                         "(auto: interleave for C5, whose period bands differ in work; block otherwise)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the other named workloads")
+    ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--inproc", action="store_true",
+                    help="ONE process driving --gpus devices through one field handle (mr_trace_many with host buffers): "
+                         "the library's own multi-device path, what mantaray.ray_tracing takes on this box")
+    ap.add_argument("--total-rays", type=int, default=0, help="--inproc: rays of the batch (0 = what the host RAM holds)")
     return ap.parse_args()
 
 
@@ -231,6 +250,55 @@ def run_reference(args):
     emit(line)
 
 
+# ---- parity of what was timed ------------------------------------------------------------------------------------
+def parity_of(wl, rays, got, cores: int):
+    """The oracle on `rays` against `got`, the same rays' columns pulled out of the buffers the timed launches
+    wrote: rows / len bit-exact, trajectories (or final states) to PARITY_TOL, position errors relative to the ray's
+    position scale and wavenumber errors to its max |k| (the metric of tests/conftest.py)."""
+    from oracle import mr_oracle as O
+
+    full = got.get("x") is not None
+    ref = O.trace_many(wl.bathymetry, wl.current, *rays, wl.t0, wl.duration, wl.dt, stride=wl.stride, nthreads=cores,
+                       trajectories=full, final_state=True)
+    equal = bool(np.array_equal(ref.rows, got["rows"]) and np.array_equal(ref.len, got["len"]))
+    worst, nan_equal = 0.0, True
+    with np.errstate(invalid="ignore"):
+        if full:
+            pos = np.nanmax(np.maximum(np.abs(ref.x), np.abs(ref.y)), axis=0, initial=0.0)
+            ksc = np.nanmax(np.hypot(ref.kx, ref.ky), axis=0, initial=0.0)
+            pos, ksc = np.where(pos > 0, pos, 1.0), np.where(ksc > 0, ksc, 1.0)
+            for name, sc in (("x", pos), ("y", pos), ("kx", ksc), ("ky", ksc)):
+                a, b = got[name], getattr(ref, name)
+                nan_equal = nan_equal and bool(np.array_equal(np.isnan(a), np.isnan(b)))
+                worst = max(worst, float(np.nanmax(np.abs(a - b) / sc[None, :], initial=0.0)))
+        f, g = ref.final_state, got["fin"]
+        nan_equal = nan_equal and bool(np.array_equal(np.isnan(f), np.isnan(g)))
+        pos = np.maximum(np.maximum(np.abs(f[0]), np.abs(f[1])), 1e-300)
+        ksc = np.maximum(np.hypot(f[2], f[3]), 1e-300)
+        for c, sc in ((0, pos), (1, pos), (2, ksc), (3, ksc)):
+            worst = max(worst, float(np.nanmax(np.abs(f[c] - g[c]) / sc, initial=0.0)))
+    return {"rays": int(rays[0].size), "rows_len_equal": equal, "nan_pattern_equal": nan_equal, "max_rel_err": worst}
+
+
+def parity_sample_size(wl, n, full, rows_cap, share=1):
+    budget = (6e6 if wl.flop_per_ray_step > 500 else 2e6) / max(share, 1)       # oracle ray-steps
+    n_par = int(min(n, max(64, budget // max(wl.n_steps, 1))))
+    if full:
+        n_par = int(min(n_par, max(64, 2.5e8 // (32 * rows_cap))))             # host copy of the sampled columns
+    return n_par
+
+
+def shard_ids(wl, name, rank, world, mode):
+    """The rays of this rank as a list of (lo, hi) index ranges of the ensemble."""
+    from mantaray_b200 import workloads as W
+
+    if mode == "auto":
+        mode = "interleave" if name == "C5" else "block"
+    if world == 1 or mode == "block":
+        return [W.shard_range(wl.n_rays, rank, world)], "block"
+    return W.shard_tiles(wl.n_rays, rank, world, wl.extra.get("tile", 16_384)), "interleave"
+
+
 def main():
     args = parse()
     claim_stdout()
@@ -242,14 +310,20 @@ def main():
 
     from mantaray_b200 import CartesianNetcdf3, _abi, _capi
     from mantaray_b200 import workloads as W
+    from tools import mrtools
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
     if world != args.gpus and world > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: mantaray_b200 has no CPU fallback")
+    if args.inproc:
+        if world > 1:
+            raise SystemExit("--inproc is ONE process driving all the devices: run it without torchrun")
+        return run_inproc(args)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -261,88 +335,29 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def allmax(v: float) -> float:
+    def allred(v: float, op) -> float:
         if world == 1:
             return v
         t = torch.tensor([v], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=op)
         return float(t.item())
 
-    def allsum(v: float) -> float:
+    allmax = lambda v: allred(v, dist.ReduceOp.MAX)
+    allmin = lambda v: allred(v, dist.ReduceOp.MIN)
+    allsum = lambda v: allred(v, dist.ReduceOp.SUM)
+
+    def allgather(v: float):
         if world == 1:
-            return v
+            return [v]
         t = torch.tensor([v], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+        out = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        return [float(o.item()) for o in out]
 
     lib = _capi.load()
     math_mode = _abi.MR_MATH_STRICT if args.math == "strict" else _abi.MR_MATH_FAST
-    wl = make_workload(args.workload, world, args.rays_per_gpu)
-    lo, hi = W.shard_range(wl.n_rays, rank, world)
-    n = hi - lo
-    x0, y0, kx0, ky0 = wl.rays(lo, hi)
-    rows_cap = wl.n_rows
-    full = wl.output == "full"
-
-    fields = _capi.Fields(wl.bathymetry, wl.current, devices=[local])
-    # ---- resident buffers --------------------------------------------------------------
-    ic = torch.from_numpy(np.stack([x0, y0, kx0, ky0])).to(dev)
-    traj = torch.empty((4, rows_cap, n), dtype=torch.float64, device=dev) if full else None
-    d_rows = torch.empty(n, dtype=torch.int32, device=dev)
-    d_len = torch.empty(n, dtype=torch.int32, device=dev)
-    d_fin = torch.empty((4, n), dtype=torch.float64, device=dev)
-    flags = {"auto": 0, "on": _abi.MR_OPT_DEEP_MAP, "off": _abi.MR_OPT_NO_DEEP_MAP}[args.deep_map]
-    opts = _abi.TraceOpts(wl.stride, math_mode, 0, flags)
-    # what the library does with those flags on this grid (include/mantaray_b200.h): the map exists on affine
-    # gridded bathymetry, and the default uses it when a quarter of its blocks are deep for a 10 s wave
-    deep_map_used, deep_share = False, None
-    if args.math == "fast" and isinstance(wl.bathymetry, CartesianNetcdf3):
-        _, deep_share, affine = _capi.depth_floor_map(wl.bathymetry)
-        deep_map_used = bool(affine) and args.deep_map != "off" and (args.deep_map == "on" or deep_share >= 0.25)
+    cores = max((os.cpu_count() or 1) // max(local_world, 1), 1)
     stream = torch.cuda.current_stream()
-    launches = C.c_int32(0)
-
-    def launch():
-        p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
-        rc = lib.mr_trace_device(fields.handle, local, C.c_void_p(stream.cuda_stream), n,
-                                 p(ic[0]), p(ic[1]), p(ic[2]), p(ic[3]),
-                                 wl.t0, wl.duration, wl.dt, C.byref(opts),
-                                 p(traj[0]) if full else None, p(traj[1]) if full else None,
-                                 p(traj[2]) if full else None, p(traj[3]) if full else None, n,
-                                 p(d_rows), p(d_len), p(d_fin), C.byref(launches))
-        if rc != 0:
-            raise RuntimeError(lib.mr_last_error().decode())
-        return launches.value
-
-    for _ in range(max(args.warmup, 3)):
-        launch()
-    torch.cuda.synchronize()
-    E_local = float((d_rows.to(torch.int64) - 1).sum().item())      # executed ray-steps per pass
-    E = allsum(E_local)
-
-    sampler = ClockSampler(local) if rank == 0 else None
-    if sampler:
-        sampler.start()
-        time.sleep(0.3)
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    barrier()
-    t_lo = time.perf_counter()
-    n_launch = 0
-    ev[0].record(stream)
-    for k in range(args.steps):
-        n_launch += launch()
-        ev[k + 1].record(stream)
-    barrier()
-    t_hi = time.perf_counter()
-    ms_total = ev[0].elapsed_time(ev[-1])
-    ms_each = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
-    ms_total = allmax(ms_total)
-    clocks = sampler.summary(t_lo, t_hi) if sampler else None
-    value = E * args.steps / (ms_total * 1e-3)
-    n_launch_total = int(allsum(float(n_launch)))          # trace kernels launched in the timed region, all ranks
-    kernel_ms = float(np.mean(ms_each))           # one kernel per step: its average launch duration
-
-    # ---- roofline of the dominant (only) kernel ----------------------------------------
     peaks = {}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -351,35 +366,182 @@ def main():
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     hbm_src = "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    fp64_peak = _capi.measure_fp64_peak(local, 200)
-    # algorithmic HBM bytes of one launch: every stored row of every ray (NaN padding included,
-    # it has to be written too) + initial state, rows/len and final state per ray
-    alg_bytes = (float(rows_cap) * n * W.BYTES_PER_ROW if full else 0.0) + n * (32 + 8 + 32)
-    alg_flop = E_local * wl.flop_per_ray_step
-    ach_tf = alg_flop / (kernel_ms * 1e-3) / 1e12
-    ach_gbs = alg_bytes / (kernel_ms * 1e-3) / 1e9
-    traffic = None                                  # DRAM bytes of one launch, from the committed ncu capture
+    fp64_peak = mrtools.measure_fp64_peak(local, 200)
+    hw_counters = {}
     try:
-        with open(os.path.join(ROOT, "profiles", "r1", "traffic.json")) as f:
-            tr = json.load(f).get(wl.name)
-        if tr and abs(tr["rays_per_gpu"] - n) <= 0.001 * n and tr["rk4_steps"] == wl.n_steps and args.math == "fast":
-            traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+        with open(os.path.join(ROOT, "profiles", "r2", "hw_counters.json")) as f:
+            hw_counters = json.load(f)
     except Exception:
         pass
-    roofline = {
-        "bound": "fp64", "kernel": "mr::trace_kernel<GRID,GRID,%s%s>" % (args.math, ",depth-floor map" if deep_map_used else ""),
-        "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_tf / fp64_peak if fp64_peak else None,
-        "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read+write); algorithmic bytes per launch = %d" % int(alg_bytes),
-        "traffic_note": ("captured on the kernel without the depth-floor map (profiles/r1/m_*); with the map the writes are "
-                         "the same and the record reads can only be fewer") if (traffic and deep_map_used) else None,
-        "flop_per_ray_step": wl.flop_per_ray_step,
-        "peak_source": "DFMA probe kernel timed in this run (mr_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
-        "kernel_ms": kernel_ms,
-    }
-    roofline_hbm = {
-        "bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
-        "traffic": traffic, "algorithmic_bytes": int(alg_bytes), "bytes_per_stored_row": W.BYTES_PER_ROW, "peak_source": hbm_src,
-    }
+    sm_count = torch.cuda.get_device_properties(local).multi_processor_count
+    flush_buf = [None]
+    flags = {"auto": 0, "on": _abi.MR_OPT_DEEP_MAP, "off": _abi.MR_OPT_NO_DEEP_MAP}[args.deep_map]
+    if args.same_grid == "off":
+        flags |= _abi.MR_OPT_NO_SAME_GRID
+
+    def run_workload(name, steps, warmup, rays_per_gpu, sampler=None):
+        """Times `steps` device-resident passes of workload `name` on this rank's share, after `warmup` untimed ones.
+        Returns (summary dict, state for the end-to-end leg)."""
+        wl = make_workload(name, world, rays_per_gpu)
+        ranges, shard_mode = shard_ids(wl, name, rank, world, args.shard)
+        parts = [wl.rays(lo, hi) for lo, hi in ranges]
+        x0, y0, kx0, ky0 = (np.concatenate([p[i] for p in parts]) for i in range(4))
+        n = x0.size
+        rows_cap = wl.n_rows
+        full = wl.output == "full"
+        fields = _capi.Fields(wl.bathymetry, wl.current, devices=[local])
+        ic = torch.from_numpy(np.stack([x0, y0, kx0, ky0])).to(dev)
+        traj = torch.empty((4, rows_cap, n), dtype=torch.float64, device=dev) if full else None
+        d_rows = torch.empty(n, dtype=torch.int32, device=dev)
+        d_len = torch.empty(n, dtype=torch.int32, device=dev)
+        d_fin = torch.empty((4, n), dtype=torch.float64, device=dev)
+        opts = _abi.TraceOpts(wl.stride, math_mode, 0, flags)
+        # what the library does with those flags on this grid (include/mantaray_b200.h): the map exists on affine
+        # gridded bathymetry, and the default uses it when a quarter of its blocks are deep for a 10 s wave
+        deep_map_used, deep_share = False, None
+        if args.math == "fast" and isinstance(wl.bathymetry, CartesianNetcdf3):
+            _, deep_share, affine = _capi.depth_floor_map(wl.bathymetry)
+            deep_map_used = bool(affine) and args.deep_map != "off" and (args.deep_map == "on" or deep_share >= 0.25)
+        launches = C.c_int32(0)
+        p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+
+        def launch():
+            rc = lib.mr_trace_device(fields.handle, local, C.c_void_p(stream.cuda_stream), n,
+                                     p(ic[0]), p(ic[1]), p(ic[2]), p(ic[3]),
+                                     wl.t0, wl.duration, wl.dt, C.byref(opts),
+                                     p(traj[0]) if full else None, p(traj[1]) if full else None,
+                                     p(traj[2]) if full else None, p(traj[3]) if full else None, n,
+                                     p(d_rows), p(d_len), p(d_fin), C.byref(launches))
+            if rc != 0:
+                raise RuntimeError(lib.mr_last_error().decode())
+            return launches.value
+
+        # L2: a pass that writes far more than the 126 MB L2 evicts everything by itself; the others get an explicit
+        # flush (a 256 MB buffer written) before every timed pass, outside the timed interval
+        out_bytes = (float(rows_cap) * n * W.BYTES_PER_ROW if full else 0.0) + n * 72.0
+        need_flush = out_bytes < 1e9
+        if need_flush and flush_buf[0] is None:
+            flush_buf[0] = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        for _ in range(max(warmup, 3)):
+            launch()
+        torch.cuda.synchronize()
+        E_local = float((d_rows.to(torch.int64) - 1).sum().item())      # executed ray-steps per pass
+        E = allsum(E_local)
+        if sampler:
+            sampler.start()
+            time.sleep(0.3)
+        ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        barrier()
+        t_lo = time.perf_counter()
+        n_launch = 0
+        for k in range(steps):
+            if need_flush:
+                flush_buf[0].zero_()
+            ev0[k].record(stream)
+            n_launch += launch()
+            ev1[k].record(stream)
+        barrier()
+        t_hi = time.perf_counter()
+        ms_each = [ev0[k].elapsed_time(ev1[k]) for k in range(steps)]
+        # the timed region: back to back from the first event to the last when nothing is flushed in between,
+        # else the sum of the per-pass intervals
+        ms_local = sum(ms_each) if need_flush else ev0[0].elapsed_time(ev1[-1])
+        per_rank_ms = [m / steps for m in allgather(ms_local)]
+        ms_total = max(per_rank_ms) * steps
+        value = E * steps / (ms_total * 1e-3)
+        kernel_ms = float(np.mean(ms_each))           # one kernel per step: its average launch duration
+        clocks = sampler.summary(t_lo, t_hi) if sampler else None
+
+        # ---- roofline of the dominant (only) kernel ----------------------------------------
+        # algorithmic HBM bytes of one launch: every stored row of every ray (NaN padding included,
+        # it has to be written too) + initial state, rows/len and final state per ray
+        alg_bytes = (float(rows_cap) * n * W.BYTES_PER_ROW if full else 0.0) + n * (32 + 8 + 32)
+        alg_flop = E_local * wl.flop_per_ray_step
+        ach_tf = alg_flop / (kernel_ms * 1e-3) / 1e12
+        ach_gbs = alg_bytes / (kernel_ms * 1e-3) / 1e9
+        variant = [args.math] + (["depth-floor map"] if deep_map_used else [])
+        kname = "mr::trace_kernel<GRID,GRID,%s>" % ",".join(variant)
+        hw, traffic = None, None
+        cap = hw_counters.get(wl.name)
+        if cap and args.math == "fast" and bool(cap.get("deep_map")) == deep_map_used and args.same_grid == "auto":
+            # the hardware's own count of the same kernel, from the committed ncu capture (a smaller launch of the same
+            # shape; per-cycle rates do not depend on the launch size)
+            fpc = cap["dadd_per_cycle"] + cap["dmul_per_cycle"] + 2.0 * cap["dfma_per_cycle"]
+            hw = {
+                "fp64_flop_per_cycle": fpc, "fp64_flop_peak_per_cycle": FP64_FLOP_PER_CLK_PER_SM * sm_count,
+                "frac_of_fp64_flop_peak": fpc / (FP64_FLOP_PER_CLK_PER_SM * sm_count),
+                "pipe_fp64_busy": cap["pipe_fp64_pct"] / 100.0,
+                "issue_active": cap.get("issue_active_pct", 0.0) / 100.0,
+                "l1_data_pipe_busy": cap.get("l1_lsu_wavefronts_pct", 0.0) / 100.0,
+                "instructions_per_rhs": cap.get("instr_per_rhs"),
+                "kernel": cap.get("kernel"), "capture": cap.get("capture"), "capture_rays": cap.get("rays"),
+                "note": "ncu smsp__sass_thread_inst_executed_op_{dadd,dmul,dfma}_pred_on per cycle: dadd + dmul + 2 dfma over "
+                        "148 SM x 128 flop/clk; pipe_fp64 = sm__inst_executed_pipe_fp64 % of peak",
+            }
+            if cap.get("traffic_rays") and abs(cap["traffic_rays"] - n) <= 0.001 * n and cap.get("rk4_steps") == wl.n_steps:
+                traffic = cap["dram_bytes_read"] + cap["dram_bytes_write"]
+        roofline = {
+            "bound": "fp64", "kernel": kname,
+            "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_tf / fp64_peak if fp64_peak else None,
+            "convention": "algorithmic: %d weighted FP64 flop per ray-step (SURVEY.md 8d: add/mul 1, div/sqrt 4, transcendental 8) "
+                          "x executed ray-steps / kernel time; the hardware-counted figure is in `hw`" % wl.flop_per_ray_step,
+            "hw": hw,
+            "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read+write); algorithmic bytes per launch = %d" % int(alg_bytes),
+            "flop_per_ray_step": wl.flop_per_ray_step,
+            "peak_source": "builder-probed: register-only DFMA kernel timed in this run (tools/libmr_tools.so, mrt_measure_fp64_peak); "
+                           "MEASURED_PEAKS.json has no FP64 entry",
+            "kernel_ms": kernel_ms,
+        }
+        roofline_hbm = {
+            "bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
+            "traffic": traffic, "algorithmic_bytes": int(alg_bytes), "bytes_per_stored_row": W.BYTES_PER_ROW, "peak_source": hbm_src,
+        }
+
+        # ---- parity: a strided sample of the buffers the timed launches wrote, against the oracle -----------
+        parity = None
+        if not args.no_parity:
+            n_par = parity_sample_size(wl, n, full, rows_cap, world)
+            sel = np.unique(np.linspace(0, n - 1, n_par).astype(np.int64))
+            sel_t = torch.from_numpy(sel).to(dev)
+            got = {"rows": d_rows[sel_t].cpu().numpy(), "len": d_len[sel_t].cpu().numpy(), "fin": d_fin[:, sel_t].cpu().numpy()}
+            if full:
+                for i, nm in enumerate(("x", "y", "kx", "ky")):
+                    got[nm] = traj[i][:, sel_t].cpu().numpy()
+            pr = parity_of(wl, (x0[sel], y0[sel], kx0[sel], ky0[sel]), got, cores)
+            pr["rays"] = int(allsum(float(pr["rays"])))
+            pr["rows_len_equal"] = bool(allmin(1.0 if pr["rows_len_equal"] else 0.0) > 0.5)
+            pr["nan_pattern_equal"] = bool(allmin(1.0 if pr["nan_pattern_equal"] else 0.0) > 0.5)
+            pr["max_rel_err"] = allmax(pr["max_rel_err"])
+            pr["tol"] = PARITY_TOL
+            pr["ok"] = bool(pr["rows_len_equal"] and pr["nan_pattern_equal"] and pr["max_rel_err"] <= PARITY_TOL)
+            pr["what"] = ("columns of the timed trajectory planes" if full else "rows / len / final states of the timed launches") + \
+                         " on a uniform stride of each rank's rays vs the C oracle (rows and len bit-exact)"
+            parity = pr
+
+        summary = {
+            "workload": wl.name, "value": value, "unit": UNIT, "ms_per_step": ms_total / steps, "steps": steps,
+            "warmup": max(warmup, 3), "rays": wl.n_rays, "rays_per_gpu": n, "rk4_steps": wl.n_steps,
+            "grid": [int(wl.bathymetry.x.size), int(wl.bathymetry.y.size)], "stride": wl.stride, "output": wl.output,
+            "executed_ray_steps_per_pass": E, "shard": shard_mode,
+            "per_rank_ms": per_rank_ms, "imbalance_max_over_mean": max(per_rank_ms) / (sum(per_rank_ms) / len(per_rank_ms)),
+            "deep_map": {"flag": args.deep_map, "used": deep_map_used, "deep_share_of_blocks": deep_share},
+            "l2": ("each pass writes %.1f GB per GPU, far more than the 126 MB L2: no flush needed" % (out_bytes / 1e9)) if not need_flush
+                  else "256 MB buffer written before every timed pass (outside the timed interval)",
+            "roofline": roofline, "roofline_hbm": roofline_hbm, "parity": parity, "gpu_launches": int(allsum(float(n_launch))),
+        }
+        state = dict(wl=wl, fields=fields, n=n, x0=x0, y0=y0, kx0=kx0, ky0=ky0, full=full, rows_cap=rows_cap, clocks=clocks,
+                     opts=opts)
+        return summary, state
+
+    # ---- the headline workload ---------------------------------------------------------------------------------
+    sampler = ClockSampler(local) if rank == 0 else None
+    head, st = run_workload(args.workload, args.steps, args.warmup, args.rays_per_gpu, sampler)
+    wl, fields, n = st["wl"], st["fields"], st["n"]
+    full, rows_cap, opts = st["full"], st["rows_cap"], st["opts"]
+    x0, y0, kx0, ky0 = st["x0"], st["y0"], st["kx0"], st["ky0"]
+    clocks = st["clocks"]
+    torch.cuda.empty_cache()            # the resident trajectories are gone: the host path allocates its own slabs
 
     # ---- end to end through the C ABI with host buffers ---------------------------------
     e2e = None
@@ -387,7 +549,6 @@ def main():
         import psutil
 
         avail = psutil.virtual_memory().available
-        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
         per_ray = 32.0 * rows_cap if full else 0.0
         budget = min(0.30 * avail / max(local_world, 1), 70e9)
         n_e2e = n if per_ray == 0 else int(min(n, max(budget // per_ray, 1024)))
@@ -411,9 +572,6 @@ def main():
             if rc != 0:
                 raise RuntimeError(lib.mr_last_error().decode())
 
-        # free the resident trajectories first: the host path allocates its own slabs
-        del traj
-        torch.cuda.empty_cache()
         e2e_call()                                              # warm-up
         e2e_steps = max(min(args.steps, 3), 1)
         barrier()
@@ -423,13 +581,37 @@ def main():
         barrier()
         el = allmax(time.perf_counter() - t0_)
         E_e2e = allsum(float((h_rows.astype(np.int64) - 1).sum()))
+        n_e2e_all = int(allsum(float(n_e2e)))
         e2e = {
             "value": E_e2e * e2e_steps / el, "unit": UNIT,
-            "h2d_bytes_per_step": int(32 * n_e2e * world),
-            "d2h_bytes_per_step": int((per_ray + 8 + 32) * n_e2e * world),
-            "rays_per_step": int(n_e2e * world), "steps": e2e_steps, "ms_per_step": 1e3 * el / e2e_steps,
+            "h2d_bytes_per_step": int(32 * n_e2e_all),
+            "d2h_bytes_per_step": int((per_ray + 8 + 32) * n_e2e_all),
+            "rays_per_step": n_e2e_all, "rays_per_step_per_rank": int(n_e2e), "steps": e2e_steps, "ms_per_step": 1e3 * el / e2e_steps,
+            "d2h_GB_per_s": (per_ray + 8 + 32) * n_e2e_all * e2e_steps / el / 1e9,
+            "batch_note": ("the per-rank batch is what 30 %% of the free host RAM / %d ranks holds as pinned planes "
+                           "(%.1f GB per rank): smaller than the %d rays per GPU of the kernel line when several ranks share the host" % (
+                               local_world, per_ray * n_e2e / 1e9, n)) if n_e2e < n else "the whole per-GPU batch",
             "api": "mr_trace_many (C ABI, pinned host buffers, H2D of the ray states and D2H of every stored row inside the timed region)",
         }
+        del h_traj
+    fields.free()
+    st = None
+
+    # ---- the other named shapes, at their BASELINE.json sizes ----------------------------------------------------
+    workloads = []
+    if not args.no_extra and not args.rays_per_gpu:
+        for name in ("C1", "C2", "C3", "C4", "C5"):
+            if name == args.workload:
+                continue
+            try:
+                s, st_x = run_workload(name, 2, 3, 0)
+                st_x["fields"].free()
+                st_x = None
+                torch.cuda.empty_cache()
+                workloads.append(s)
+            except Exception as e:           # an extra never takes the headline line down with it
+                workloads.append({"workload": name, "error": f"{type(e).__name__}: {e}"})
+            barrier()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -440,27 +622,120 @@ def main():
         sampler.stop()
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT,
+            "metric": METRIC, "value": head["value"], "unit": UNIT,
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {
                 "workload": wl.name, "description": wl.description, "rays": wl.n_rays, "rays_per_gpu": n,
-                "rk4_steps": wl.n_steps, "grid": [int(wl.bathymetry.x.size), int(wl.bathymetry.y.size)],
+                "rk4_steps": wl.n_steps, "grid": head["grid"],
                 "stride": wl.stride, "output": wl.output, "math": args.math,
-                "deep_map": {"flag": args.deep_map, "used": deep_map_used, "deep_share_of_blocks": deep_share},
-                "executed_ray_steps_per_pass": E, "parallelism": f"rays sharded x{world}, fields replicated, no collective",
-                "l2": "no flush needed: each pass writes %.1f GB of trajectories per GPU, far larger than the 126 MB L2" % (
-                    rows_cap * n * 32 / 1e9) if full else "final-state only: inputs (fields %.0f MB) re-read each pass" % (
-                    wl.bathymetry.depth.nbytes * 3 / 1e6),
+                "deep_map": head["deep_map"], "same_grid": args.same_grid,
+                "executed_ray_steps_per_pass": head["executed_ray_steps_per_pass"],
+                "parallelism": f"rays sharded x{world} ({head['shard']}), fields replicated, no collective",
+                "l2": head["l2"],
             },
-            "roofline": roofline, "roofline_hbm": roofline_hbm,
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": n_launch_total, "clocks": clocks,
+            "roofline": head["roofline"], "roofline_hbm": head["roofline_hbm"],
+            "parity": head["parity"],
+            "per_rank_ms": head["per_rank_ms"], "imbalance_max_over_mean": head["imbalance_max_over_mean"],
+            "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": head["gpu_launches"], "clocks": clocks,
+            "workloads": workloads,
         }
         emit(line)
-    fields.free()
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_inproc(args):
+    """ONE process, one field handle on --gpus devices, mr_trace_many with pinned host buffers: the library's own
+    multi-device path (a shared queue of slabs, one worker thread per device).  End to end by construction: the
+    ray states go up and every stored row comes down inside the timed region."""
+    import psutil
+
+    from mantaray_b200 import _abi, _capi
+
+    lib = _capi.load()
+    G = max(args.gpus, 1)
+    if _capi.device_count() < G:
+        raise SystemExit(f"--gpus {G} but {_capi.device_count()} device(s) visible")
+    # the ensemble of the N-GPU weak-scaling run; --total-rays fixes the batch instead (strong scaling over --gpus)
+    wl = make_workload(args.workload, 8 if args.total_rays else G, args.rays_per_gpu)
+    rows_cap, full = wl.n_rows, wl.output == "full"
+    per_ray = 32.0 * rows_cap if full else 0.0
+    avail = psutil.virtual_memory().available
+    n = wl.n_rays if per_ray == 0 else int(min(wl.n_rays, max(0.55 * avail // per_ray, 1024)))
+    if args.total_rays:
+        n = min(n, args.total_rays)
+    # a uniform stride over the ensemble, so that a shortened batch keeps the variety of the whole one
+    step = max(wl.n_rays // n, 1)
+    x0a, y0a, kx0a, ky0a = wl.rays(0, wl.n_rays)
+    sel = slice(0, step * n, step)
+    hx0 = _capi.pinned_empty((4, n))
+    hx0[0], hx0[1], hx0[2], hx0[3] = x0a[sel], y0a[sel], kx0a[sel], ky0a[sel]
+    del x0a, y0a, kx0a, ky0a
+    h_t = np.empty(rows_cap)
+    h_traj = _capi.pinned_empty((4, rows_cap, n)) if full else None
+    h_rows = _capi.pinned_empty((n,), np.int32)
+    h_len = _capi.pinned_empty((n,), np.int32)
+    h_fin = _capi.pinned_empty((4, n))
+    math_mode = _abi.MR_MATH_STRICT if args.math == "strict" else _abi.MR_MATH_FAST
+    flags = {"auto": 0, "on": _abi.MR_OPT_DEEP_MAP, "off": _abi.MR_OPT_NO_DEEP_MAP}[args.deep_map]
+    opts = _abi.TraceOpts(wl.stride, math_mode, 0, flags)
+    pp = lambda a: a.ctypes.data if a is not None else None
+    fields = _capi.Fields(wl.bathymetry, wl.current, devices=list(range(G)))
+
+    def call():
+        rc = lib.mr_trace_many(fields.handle, n, pp(hx0[0]), pp(hx0[1]), pp(hx0[2]), pp(hx0[3]),
+                               wl.t0, wl.duration, wl.dt, C.byref(opts), pp(h_t),
+                               pp(h_traj[0]) if full else None, pp(h_traj[1]) if full else None,
+                               pp(h_traj[2]) if full else None, pp(h_traj[3]) if full else None,
+                               pp(h_rows), pp(h_len), pp(h_fin))
+        if rc != 0:
+            raise RuntimeError(lib.mr_last_error().decode())
+
+    sampler = ClockSampler(0)
+    call()                                                      # warm-up: allocates the slabs, pages the planes in
+    sampler.start()
+    time.sleep(0.3)
+    steps = max(min(args.steps, 3), 1)
+    t_lo = time.perf_counter()
+    for _ in range(steps):
+        call()
+    t_hi = time.perf_counter()
+    sampler.stop()
+    el = t_hi - t_lo
+    E = float((h_rows.astype(np.int64) - 1).sum())
+    split = fields.last_split()
+    parity = None
+    if not args.no_parity:
+        n_par = parity_sample_size(wl, n, full, rows_cap)
+        s2 = np.unique(np.linspace(0, n - 1, n_par).astype(np.int64))
+        got = {"rows": h_rows[s2].copy(), "len": h_len[s2].copy(), "fin": h_fin[:, s2].copy()}
+        if full:
+            for i, nm in enumerate(("x", "y", "kx", "ky")):
+                got[nm] = h_traj[i][:, s2].copy()
+        parity = parity_of(wl, tuple(hx0[i][s2].copy() for i in range(4)), got, os.cpu_count() or 1)
+        parity["tol"] = PARITY_TOL
+        parity["ok"] = bool(parity["rows_len_equal"] and parity["nan_pattern_equal"] and parity["max_rel_err"] <= PARITY_TOL)
+    fields.free()
+    d2h = (per_ray + 8 + 32) * n
+    val = E * steps / el
+    emit({
+        "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": G, "steps": steps, "warmup": 1,
+        "ms_per_step": 1e3 * el / steps, "higher_is_better": True, "scaling": "strong" if args.total_rays else "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "mode": "inproc",
+        "config": {"workload": wl.name, "description": wl.description, "rays": n, "rays_of_ensemble": wl.n_rays, "rk4_steps": wl.n_steps,
+                   "grid": [int(wl.bathymetry.x.size), int(wl.bathymetry.y.size)], "stride": wl.stride, "output": wl.output,
+                   "math": args.math, "parallelism": f"one process, one handle on {G} device(s), shared slab queue, no collective"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": int(32 * n), "d2h_bytes_per_step": int(d2h),
+                "d2h_GB_per_s": d2h * steps / el / 1e9, "rays_per_step": n,
+                "api": "mr_trace_many (C ABI, host buffers; every device of the handle works on the same call)"},
+        "rays_taken_per_device_last_call": split,
+        "split_max_over_mean": (max(split) / (sum(split) / len(split))) if split and sum(split) else None,
+        "parity": parity, "gpu_launches": None, "clocks": sampler.summary(t_lo, t_hi),
+        "executed_ray_steps_per_pass": E,
+    })
 
 
 if __name__ == "__main__":

@@ -132,6 +132,13 @@ typedef struct mr_trace_opts {
  *   MR_OPT_NO_DEEP_MAP : never use it (wins over MR_OPT_DEEP_MAP)                                     */
 #define MR_OPT_DEEP_MAP    1
 #define MR_OPT_NO_DEEP_MAP 2
+/* Same-grid shortcut.  When the current is given on the bathymetry's own grid (same shape, same coordinates)
+ * MR_MATH_FAST derives the current's cell from the bathymetry's f32 fractional index wherever that index is
+ * further from a grid line than the two indices of the reference (f32 for the bathymetry, f64 for the current)
+ * can disagree, and evaluates both lookups separately elsewhere: the same cells, hence the same values, with one
+ * index and one cell geometry instead of two.  On by default where it applies.
+ *   MR_OPT_NO_SAME_GRID : always evaluate the two lookups separately                                  */
+#define MR_OPT_NO_SAME_GRID 4
 
 /* ---- library ------------------------------------------------------------- */
 
@@ -163,6 +170,13 @@ void mr_fields_free(mr_fields *f);
 /* Devices the handle lives on, as a bit mask. */
 uint32_t mr_fields_device_mask(const mr_fields *f);
 
+/* How the last host-buffer call on this handle (mr_trace_many, mr_trace_many_env)
+ * was shared out: rays_per_device[g] receives the number of rays the g-th device
+ * of the mask (ascending device number) took from the slab queue.  Returns the
+ * number of devices in the handle (entries beyond `cap` are not written), or
+ * MR_ERR_BAD_ARG. */
+int  mr_fields_last_split(mr_fields *f, int64_t *rays_per_device, int32_t cap);
+
 /* The host-buffer entry points (mr_trace_many, mr_trace_many_env, mr_single_ray)
  * keep their device work buffers in the handle so that the next call does not
  * allocate again: up to two slabs of <= 16 GB per device.  This gives them back
@@ -173,8 +187,10 @@ void mr_fields_trim(mr_fields *f);
 
 /* Number of RK4 steps the stepper takes: ceil((t_end - t0)/dt)
  * (ode_solvers 0.4.0 Rk4::integrate; called from src/ray.rs:207-208).
- * Returns -1 if dt is not > 0 or the quotient is not finite / negative
- * (the reference panics on those). */
+ * A negative quotient (t_end < t0) is 0 steps: the reference's
+ * `((x_end - x) / h).ceil() as usize` saturates it, and the ray is its initial
+ * row only.  Returns -1 if dt is not > 0, or the quotient is NaN, infinite or
+ * >= 2^31 - 2 (the reference panics or never returns on those). */
 int64_t mr_num_steps(double t0, double t_end, double dt);
 /* Rows a trajectory buffer must hold: num_steps/stride + 1. */
 int64_t mr_num_rows(double t0, double t_end, double dt, int32_t stride);
@@ -183,8 +199,12 @@ int64_t mr_num_rows(double t0, double t_end, double dt, int32_t stride);
 
 /*
  * ManyRays::trace_many (src/ray.rs:98-127) for n rays, initial states
- * (x0[i], y0[i], kx0[i], ky0[i]).  Rays are split in contiguous blocks over
- * the devices of the handle; there is no cross-ray communication.
+ * (x0[i], y0[i], kx0[i], ky0[i]).  With several devices in the handle the batch
+ * is one queue of contiguous slabs of rays and every device takes the next slab
+ * when it has a free buffer — the dynamic balance rayon's par_iter gives the
+ * reference (src/ray.rs:105-123), so rays that stop early do not leave a device
+ * idle.  There is no cross-ray communication; each slab is copied into its
+ * column block of the outputs.
  *
  * Outputs (all HOST memory, caller-owned, any of them may be NULL):
  *   t [rows_cap]            time of row j: t0, then accumulated += dt*stride steps
@@ -305,23 +325,7 @@ int  mr_nc3_read_f64(const mr_nc3 *f, const char *name, double *out, int64_t cap
 int  mr_host_alloc(size_t bytes, void **out);
 void mr_host_free(void *p);
 
-/* ---- measurement aids ----------------------------------------------------- */
-
-/* Sustained FP64 FMA throughput of `device` in TFLOP/s (2 flop per DFMA),
- * measured with a register-only DFMA kernel timed by CUDA events over
- * `millis` ms of work.  This is the denominator of the FP64 roofline; it is
- * measurement plumbing, not part of the path. */
-int  mr_measure_fp64_peak(int device, int millis, double *tflops);
-
-/* Self-test of the fast path's exact f32 division by a launch constant (the fractional
- * index of src/bathymetry/cartesian_netcdf3.rs:289): compares it with the IEEE divide for
- * EVERY non-negative finite float t, for the divisor `spacing`, on `device`.  *mismatches
- * receives the number of t whose quotients differ in any bit, except that an infinite
- * quotient may come out as NaN (both are out of bounds) and that for 0 < t < 2^-100 (where
- * the exact residual underflows) both quotients only have to lie in [0, 1), i.e. cell 0 and in
- * bounds either way; *usable receives 0 if the library would not use the shortcut for this
- * spacing. */
-int  mr_selftest_fdiv(int device, float spacing, uint64_t *mismatches, int32_t *usable);
+/* ---- inspection ------------------------------------------------------------ */
 
 /* The depth-floor map MR_OPT_DEEP_MAP consults, as the library builds it for a GRID bathymetry at upload:
  * one float per block of 8 x 8 cells, row-major [*nby][*nbx], holding the square (rounded down) of a lower

@@ -72,6 +72,7 @@ class CurrentDesc(C.Structure):
 
 MR_OPT_DEEP_MAP = 1
 MR_OPT_NO_DEEP_MAP = 2
+MR_OPT_NO_SAME_GRID = 4
 
 
 class TraceOpts(C.Structure):
@@ -153,10 +154,9 @@ SIGNATURES = {
     ),
     "mr_nc3_read_f32": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64]),
     "mr_nc3_read_f64": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64]),
+    "mr_fields_last_split": (C.c_int, [C.c_void_p, c_int64_p, C.c_int32]),
     "mr_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
     "mr_host_free": (None, [C.c_void_p]),
-    "mr_measure_fp64_peak": (C.c_int, [C.c_int, C.c_int, c_double_p]),
-    "mr_selftest_fdiv": (C.c_int, [C.c_int, C.c_float, C.POINTER(C.c_uint64), c_int32_p]),
     "mr_depth_floor_map": (C.c_int, [C.POINTER(BathymetryDesc), C.c_void_p, C.c_size_t, c_int32_p, c_int32_p,
                                      C.POINTER(C.c_float), c_int32_p]),
 }

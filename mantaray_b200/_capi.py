@@ -34,6 +34,11 @@ class MantarayError(RuntimeError):
 
 
 def lib_path() -> str:
+    """The in-tree CUDA extension.  ``MANTARAY_B200_LIB`` points at another build of the same ABI (the A/B
+    variants of ``make VARIANT=...``); it is still this library's sm_100a code, never a fallback."""
+    override = os.environ.get("MANTARAY_B200_LIB")
+    if override:
+        return os.path.abspath(override)
     return os.path.join(os.path.dirname(os.path.abspath(__file__)), _LIB_NAME)
 
 
@@ -185,6 +190,14 @@ class Fields:
     def device_mask(self) -> int:
         return int(self._lib.mr_fields_device_mask(self.handle))
 
+    def last_split(self):
+        """Rays each device of the handle took in the last host-buffer call (``mr_fields_last_split``)."""
+        out = (C.c_int64 * 32)()
+        n = int(self._lib.mr_fields_last_split(self.handle, out, 32))
+        if n < 0:
+            _check(n)
+        return [int(out[i]) for i in range(n)]
+
     def trim(self) -> None:
         """Give the cached device work buffers of the host-buffer path back (``mr_fields_trim``)."""
         if self._h:
@@ -238,7 +251,7 @@ class TraceResult:
 def num_steps(t0: float, t_end: float, dt: float) -> int:
     n = int(load().mr_num_steps(t0, t_end, dt))
     if n < 0:
-        raise ValueError("need step_size > 0 and 0 <= (end - start)/step_size < 2**31")
+        raise ValueError("need step_size > 0 and a finite (end - start)/step_size < 2**31")
     return n
 
 
@@ -327,12 +340,6 @@ def single_ray(fields: Fields, x0: float, y0: float, kx0: float, ky0: float,
                              float(t0), float(t_end), float(dt), C.byref(o),
                              out.ctypes.data, cap, C.byref(n_rows)))
     return out[: n_rows.value]
-
-
-def measure_fp64_peak(device: int = 0, millis: int = 200) -> float:
-    v = C.c_double()
-    _check(load().mr_measure_fp64_peak(device, millis, C.byref(v)))
-    return float(v.value)
 
 
 # ---- the batch driver, mirroring src/ray.rs ------------------------------------------------

@@ -20,11 +20,85 @@ Differences a caller can observe:
 from __future__ import annotations
 
 import os
+import threading
+from collections import OrderedDict
 
 import numpy as np
 
 from . import _capi
 from ._abi import MR_MATH_FAST
+
+# ---- field-handle cache ----------------------------------------------------------------------------------------
+# The reference opens and parses both NetCDF files on every call (src/ffi.rs:36-38, :62-64).  Here a call leaves its
+# field handle — the grids resident on the devices, their cell records, the work buffers of the host path — in a small
+# LRU cache keyed on what identifies the inputs: (real path, size, mtime in ns) of both files and the device set.  A
+# repeated call, the usual notebook pattern (same fields, new rays), then skips the parse, the upload and the record
+# build.  A file that is rewritten gets a new key.  `MANTARAY_B200_CACHE=<n>` sets the number of handles kept
+# (default 2, 0 disables); `clear_cache()` frees them now.  Only the most recent handle keeps its work buffers.
+_CACHE: "OrderedDict[tuple, _capi.Fields]" = OrderedDict()
+_CACHE_LOCK = threading.Lock()
+_CACHE_STATS = {"hits": 0, "misses": 0}
+
+
+def _cache_capacity() -> int:
+    try:
+        return max(int(os.environ.get("MANTARAY_B200_CACHE", "2")), 0)
+    except ValueError:
+        return 2
+
+
+def _file_key(path):
+    if path is None:
+        return None
+    st = os.stat(path)                       # a missing file raises here as it would at open: FileNotFoundError is an OSError
+    return (os.path.realpath(path), st.st_size, st.st_mtime_ns)
+
+
+def clear_cache() -> None:
+    """Free every cached field handle (device memory included)."""
+    with _CACHE_LOCK:
+        while _CACHE:
+            _CACHE.popitem(last=False)[1].free()
+
+
+def cache_info() -> dict:
+    with _CACHE_LOCK:
+        return {"entries": len(_CACHE), "capacity": _cache_capacity(), **_CACHE_STATS}
+
+
+class _Borrowed:
+    """Context manager over a cached (not freed on exit) or a private (freed on exit) handle."""
+
+    def __init__(self, fields, owned: bool):
+        self.fields, self.owned = fields, owned
+
+    def __enter__(self):
+        return self.fields
+
+    def __exit__(self, *exc):
+        if self.owned:
+            self.fields.free()
+
+
+def _open_fields(bathymetry_filename: str, current_filename: str, dev) -> _Borrowed:
+    cap = _cache_capacity()
+    if cap == 0:
+        return _Borrowed(_capi.Fields.open_netcdf3(bathymetry_filename, current_filename, devices=dev), True)
+    key = (_file_key(bathymetry_filename), _file_key(current_filename), tuple(dev))
+    with _CACHE_LOCK:
+        f = _CACHE.get(key)
+        if f is not None:
+            _CACHE.move_to_end(key)
+            _CACHE_STATS["hits"] += 1
+            return _Borrowed(f, False)
+        _CACHE_STATS["misses"] += 1
+        f = _capi.Fields.open_netcdf3(bathymetry_filename, current_filename, devices=dev)
+        for old in _CACHE.values():
+            old.trim()                       # only the newest handle keeps its slabs
+        _CACHE[key] = f
+        while len(_CACHE) > cap:
+            _CACHE.popitem(last=False)[1].free()
+        return _Borrowed(f, False)
 
 
 def _devices():
@@ -66,7 +140,7 @@ def single_ray(x0: float, y0: float, kx0: float, ky0: float, duration: float, st
                bathymetry_filename: str, current_filename: str) -> np.ndarray:
     """src/ffi.rs:25-49.  ``t0 = 0`` (:41)."""
     dev = _devices()[:1]
-    with _capi.Fields.open_netcdf3(str(bathymetry_filename), str(current_filename), devices=dev) as f:
+    with _open_fields(str(bathymetry_filename), str(current_filename), dev) as f:
         return _capi.single_ray(f, x0, y0, kx0, ky0, 0.0, duration, step_size, math=MR_MATH_FAST)
 
 
@@ -80,6 +154,6 @@ def ray_tracing(x0, y0, kx0, ky0, duration: float, step_size: float,
     dev = _devices()
     if n < 4096:                         # not worth more than one device
         dev = dev[:1]
-    with _capi.Fields.open_netcdf3(str(bathymetry_filename), str(current_filename), devices=dev) as f:
+    with _open_fields(str(bathymetry_filename), str(current_filename), dev) as f:
         res = _capi.trace_many(f, x0, y0, kx0, ky0, 0.0, duration, step_size, math=MR_MATH_FAST, pinned=None, env=env)
     return RayBundle(res)

@@ -20,7 +20,11 @@
 #include <cstring>
 #include <limits>
 #include <memory>
+#include <atomic>
 #include <mutex>
+#include <new>
+#include <stdexcept>
+#include <system_error>
 #include <thread>
 
 #include "mr_internal.hpp"
@@ -37,6 +41,24 @@ int fail(int code, const std::string &msg)
     g_err = msg;
     return code;
 }
+// No exception crosses the C ABI ("no unwinding across the ABI").  Every extern "C" body that can
+// allocate runs between MR_API_BEGIN and MR_API_END; this maps whatever was thrown to a status code.
+static int translate_exception(const char *where) noexcept
+{
+    try {
+        try { throw; }
+        catch (const std::bad_alloc &) { return fail(MR_ERR_OOM, std::string(where) + ": out of host memory"); }
+        catch (const std::length_error &e) { return fail(MR_ERR_OOM, std::string(where) + ": size too large for host memory (" + e.what() + ")"); }
+        catch (const std::system_error &e) { return fail(MR_ERR_OOM, std::string(where) + ": could not start a host thread (" + e.what() + ")"); }
+        catch (const std::exception &e) { return fail(MR_ERR_FORMAT, std::string(where) + ": " + e.what()); }
+        catch (...) { return fail(MR_ERR_FORMAT, std::string(where) + ": unknown C++ exception"); }
+    } catch (...) {
+        return MR_ERR_OOM;             // even the message could not be built
+    }
+}
+#define MR_API_BEGIN try {
+#define MR_API_END(where) } catch (...) { return mr::translate_exception(where); }
+
 static int cuda_fail(cudaError_t e, const char *what)
 {
     int code = (e == cudaErrorMemoryAllocation) ? MR_ERR_OOM : MR_ERR_CUDA;
@@ -47,49 +69,6 @@ static int cuda_fail(cudaError_t e, const char *what)
         cudaError_t e__ = (call);                                     \
         if (e__ != cudaSuccess) return cuda_fail(e__, #call);         \
     } while (0)
-
-// ---- DFMA probe -------------------------------------------------------------
-__global__ void __launch_bounds__(256) dfma_probe_kernel(double *sink, int iters)
-{
-    // 8 independent chains per thread keep the FP64 pipe full at any occupancy
-    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3;
-    double a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
-    const double m = 0.999999999, c = 1e-12;
-    for (int i = 0; i < iters; ++i) {
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
-            a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
-        }
-    }
-    double s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
-    if (s == 123.456) sink[0] = s;     // never true; keeps the chains alive
-}
-cudaError_t launch_dfma_probe(double *sink, int iters, int blocks, cudaStream_t stream)
-{
-    dfma_probe_kernel<<<blocks, 256, 0, stream>>>(sink, iters);
-    return cudaGetLastError();
-}
-
-// ---- exhaustive check of fdiv_const ---------------------------------------------
-__global__ void fdiv_selftest_kernel(float s, float r, unsigned long long *bad)
-{
-    unsigned long long local = 0;
-    // every non-negative finite float: bit patterns 0 .. 0x7f7fffff
-    for (unsigned long long b = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; b <= 0x7f7fffffull;
-         b += (unsigned long long)gridDim.x * blockDim.x) {
-        const float t = __uint_as_float((unsigned)b);
-        const float want = __fdiv_rn(t, s), got = fdiv_const(t, s, r);
-        // Below |t| = 2^-100 the exact residual t - q*s underflows and the last bits of the
-        // quotient may differ; there (s > 1e-30 is enforced) both quotients are in [0, 1): cell 0
-        // and in bounds either way, which is all the caller derives from the index.
-        const bool tiny = t > 0.0f && t < 7.8886090522101181e-31f;
-        const bool same = (__float_as_uint(want) == __float_as_uint(got)) || (isinf(want) && !(got == got)) ||
-                          (!(want == want) && !(got == got)) || (tiny && want < 1.0f && got >= 0.0f && got < 1.0f);
-        local += same ? 0 : 1;
-    }
-    if (local) atomicAdd(bad, local);
-}
 
 // ---- field handle -----------------------------------------------------------
 // Work memory of the host-buffer path (mr_trace_many), kept by the handle between calls: allocating and
@@ -107,6 +86,8 @@ struct DeviceFields {
     BathyDev b{};
     CurrentDev c{};
     float deep_frac = 0.0f;    // share of the depth-floor map's blocks that are deep water for a 10 s wave
+    size_t max_pitch = 0;      // cudaDevAttrMaxPitch: the largest pitch cudaMemcpy2D accepts
+    int64_t last_taken = 0;    // rays this device took from the slab queue in the last host-buffer call
     std::vector<void *> allocs;
     WorkArea work;             // guarded by mr_fields::mu
 };
@@ -244,17 +225,23 @@ static bool affine_f32(const float *c, int n, float *d_out)
 }
 
 // Depth-floor map of the fast path (FastRay, DMAP): for every block of kDeepBlock x kDeepBlock cells, the square
-// (rounded down) of H = zmin - 1e-5 zmax over the f32 depths of all nodes the block's cells touch.  The f32
-// bilinear of interpolator.rs:59-83 returns, inside a cell, a value between its corners up to a few roundings of
-// terms no larger than ~2 zmax (< 1e-6 zmax), so every depth the lookup can produce in the block is >= H.
+// (rounded down) of a lower bound H of every depth the f32 bilinear of interpolator.rs:59-83 can return for a
+// point the lookup assigns to one of the block's cells, over the f32 depths of all nodes those cells touch:
+//   H = zmin - 1e-5 zmax - max(nx, ny) 2^-22 (zmax - zmin).
+// Inside a cell the bilinear returns a value between its corners up to a few roundings of terms no larger than
+// ~2 zmax: the first margin (< 1e-6 zmax needed).  The second covers extrapolation: the cell is floor() of an f32
+// fractional index that carries a rounding error of up to i 2^-24 cells, so a point up to that far OUTSIDE cell i
+// can be assigned to it (the index rounds up to the integer), its basis coordinate is then negative by that much
+// (or exceeds 1), and the bilinear extrapolates beyond the corner values by up to ~2 i 2^-24 (zmax - zmin).
 // A block with a node that is NaN, infinite or <= 0 gets 0: no bound, the kernel looks the depth up.
-// *deep_frac: the share of blocks with H >= 550 m (kh >= 22 for periods up to ~10 s), what an automatic choice
-// of MR_OPT_DEEP_MAP would look at.
+// *deep_frac: the share of blocks with H >= 550 m (kh >= 22 for periods up to ~10 s), what the automatic choice
+// of MR_OPT_DEEP_MAP looks at.
 static std::vector<float> depth_floor_map(const double *depth, int nx, int ny, int *nbx_out, int *nby_out, float *deep_frac)
 {
     size_t n_deep = 0;
     const int B = kDeepBlock;
     const int nbx = (nx - 1 + B - 1) / B, nby = (ny - 1 + B - 1) / B;
+    const double extrap = (double)std::max(nx, ny) * 0x1p-22;
     std::vector<float> out((size_t)nbx * (size_t)nby, 0.0f);
     for (int by = 0; by < nby; ++by) {
         const int j0 = by * B, j1 = std::min(j0 + B, ny - 1);          // nodes j0..j1 inclusive
@@ -269,7 +256,7 @@ static std::vector<float> depth_floor_map(const double *depth, int nx, int ny, i
                     zmin = std::min(zmin, z); zmax = std::max(zmax, z);
                 }
             if (bad) continue;
-            const double H = (double)zmin - 1e-5 * (double)zmax;
+            const double H = (double)zmin - 1e-5 * (double)zmax - extrap * ((double)zmax - (double)zmin);
             if (!(H > 0.0)) continue;
             const double sq = H * H;
             float v = sq >= (double)FLT_MAX ? FLT_MAX : (float)sq;
@@ -295,18 +282,6 @@ static bool basis_coeffs(float dx, float dy, float *c01, float *c10)
     return std::isfinite(*c01) && std::isfinite(*c10);
 }
 
-// RN(1/s) for fdiv_const; refused for subnormal / huge s and for the all-ones significand
-// that Markstein's theorem excludes
-static bool recip_ok(float s, float *r)
-{
-    uint32_t bits;
-    std::memcpy(&bits, &s, 4);
-    if (!(s > 1e-30f) || !(s < 1e30f) || (bits & 0x7fffffu) == 0x7fffffu) return false;
-    volatile float q = 1.0f / s;
-    *r = q;
-    return true;
-}
-
 template <typename T>
 static int device_alloc(DeviceFields &d, size_t count, T **out)
 {
@@ -320,6 +295,12 @@ static int device_alloc(DeviceFields &d, size_t count, T **out)
 static int upload_fields(DeviceFields &d, const mr_bathymetry_desc *b, const mr_current_desc *c)
 {
     MR_CUDA(cudaSetDevice(d.dev));
+    {
+        int mp = 0;
+        MR_CUDA(cudaDeviceGetAttribute(&mp, cudaDevAttrMaxPitch, d.dev));
+        d.max_pitch = (size_t)std::max(mp, 0);
+        if (const char *e = std::getenv("MR_DEBUG_MAX_PITCH")) d.max_pitch = (size_t)std::strtoull(e, nullptr, 10);   // tests: force the row-by-row gather
+    }
     BathyDev &B = d.b;
     B.kind = b->kind; B.nx = b->nx; B.ny = b->ny;
     B.h0 = b->h0; B.x0 = b->x0; B.y0 = b->y0; B.dhdx = b->dhdx; B.dhdy = b->dhdy;
@@ -401,6 +382,26 @@ static int upload_fields(DeviceFields &d, const mr_bathymetry_desc *b, const mr_
         };
         C.p0 = pack2c(C.xf0, C.yf0); C.d2 = pack2c(C.dxf, C.dyf); C.c2 = pack2c(C.c10, C.c01);
     }
+    // Same-grid shortcut (FastRay, SG): the current lives on the bathymetry's grid — same shape, bit-identical f32
+    // coordinates and basis, f64 coordinates that are exactly the f32 ones widened — so one f32 fractional index
+    // serves both fields wherever it lies further than sg_delta from an integer.  Around the exact index I the
+    // f32 one (position rounded to f32, f32 subtraction, correctly rounded f32 quotient) is off by at most
+    // 2^-24 (3 n + |x0|/s) (1 + 2^-22), the f64 one by 2^-51 n; the distance itself is formed in f32 with an error
+    // below 2^-25.  sg_delta is that bound with a 2 % margin plus 2^-22.
+    B.same_grid = 0; B.sg_lim = 0.0f;
+    if (b->kind == MR_BATHY_GRID && c->kind == MR_CURRENT_GRID && B.uniform && C.uniform &&
+        b->nx == c->nx && b->ny == c->ny && B.p0 == C.p0 && B.d2 == C.d2 && B.c2 == C.c2 &&
+        C.xd0 == (double)B.xf0 && C.yd0 == (double)B.yf0 && C.sx == (double)B.sx && C.sy == (double)B.sy &&
+        C.x_space > 0.0 && C.y_space > 0.0) {
+        const double dx = 0x1p-24 * (3.0 * b->nx + std::fabs((double)B.xf0) / (double)B.sx) * 1.02 + 0x1p-22;
+        const double dy = 0x1p-24 * (3.0 * b->ny + std::fabs((double)B.yf0) / (double)B.sy) * 1.02 + 0x1p-22;
+        const double delta = std::max(dx, dy);
+        if (delta < 0.125) {
+            float lim = (float)(0.5 - delta);
+            if ((double)lim > 0.5 - delta) lim = std::nextafterf(lim, 0.0f);
+            B.same_grid = 1; B.sg_lim = lim;
+        }
+    }
     MR_CUDA(cudaDeviceSynchronize());
     return MR_OK;
 }
@@ -472,6 +473,7 @@ static int enqueue_trace(const DeviceFields &d, cudaStream_t stream, int64_t n,
     a.x = x; a.y = y; a.kx = kx; a.ky = ky; a.ld = ld;
     a.rows = rows; a.len = len; a.fin = fin;
     a.deep_map = want_deep_map(d, o);
+    a.same_grid = !(o.flags & MR_OPT_NO_SAME_GRID);
     cudaError_t e;
     if (o.math == MR_MATH_STRICT) e = launch_trace_strict(a, stream);
     else if (o.math == MR_MATH_FAST) e = launch_trace_fast(a, stream);
@@ -523,13 +525,39 @@ static size_t carve(DevBuf &B, char *base, int64_t chunk, int64_t rows_cap, bool
     return off;
 }
 
-// Traces rays [lo, hi) on device d.  Rays are cut into slabs of `chunk` rays;
-// slab k+1 integrates on the compute stream while slab k drains to the host on
-// the copy stream (two device buffers).  Buffers, streams and events live in the
-// handle's WorkArea and are reused by the next call.
-static int trace_block_on_device(DeviceFields &d, const HostJob &j, int64_t lo, int64_t hi, std::string &err)
+// Rays are handed out in slabs from one shared cursor (the whole batch is one queue): a device takes the next
+// slab when one of its two buffers is free, so a device whose rays stop early simply takes more slabs.  This is
+// the dynamic balance rayon's work-stealing par_iter gives the reference (src/ray.rs:105-123); a static split
+// into one contiguous block per device leaves whole period bands of a frequency/direction ensemble (C5) on one
+// device.  Slabs are contiguous in input order, so the gather stays a concatenation of column blocks.
+struct SlabQueue {
+    std::atomic<int64_t> next{0};
+    std::atomic<bool> failed{false};
+    int64_t n = 0;
+    int devices = 1;
+};
+
+// D2H copy of `height` rows of `width` bytes into a column block of a wider host plane.  cudaMemcpy2DAsync refuses
+// pitches above cudaDevAttrMaxPitch (~2 GiB: more than 2.68e8 rays per row of doubles); beyond it the rows go one
+// by one.
+static cudaError_t copy_columns_d2h(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t height,
+                                    size_t max_pitch, cudaStream_t s)
 {
-    auto bail = [&](int code, const std::string &m) { err = m; return code; };
+    if (dpitch <= max_pitch && spitch <= max_pitch)
+        return cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, cudaMemcpyDeviceToHost, s);
+    for (size_t r = 0; r < height; ++r) {
+        cudaError_t e = cudaMemcpyAsync((char *)dst + r * dpitch, (const char *)src + r * spitch, width, cudaMemcpyDeviceToHost, s);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+// One device's worker: takes slabs of `chunk` rays from the queue until it is empty.  Slab k+1 integrates on the
+// compute stream while slab k drains to the host on the copy stream (two device buffers).  Buffers, streams and
+// events live in the handle's WorkArea and are reused by the next call.
+static int trace_slabs_on_device(DeviceFields &d, const HostJob &j, SlabQueue &q, std::string &err)
+{
+    auto bail = [&](int code, const std::string &m) { err = m; q.failed.store(true); return code; };
 #define MR_TRY(call)                                                                      \
     do {                                                                                  \
         cudaError_t e__ = (call);                                                         \
@@ -541,7 +569,7 @@ static int trace_block_on_device(DeviceFields &d, const HostJob &j, int64_t lo, 
     } while (0)
 
     int rc = MR_OK;
-    const int64_t n = hi - lo;
+    const int64_t n = q.n;
     if (n <= 0) return MR_OK;
     // MR_DEBUG_TIMING=1: where a host-buffer call spends its wall time (stderr)
     static const bool timing = std::getenv("MR_DEBUG_TIMING") != nullptr;
@@ -549,10 +577,12 @@ static int trace_block_on_device(DeviceFields &d, const HostJob &j, int64_t lo, 
     const auto t_begin = clk::now();
     auto t_alloc = t_begin, t_enqueued = t_begin, t_synced = t_begin;
     const bool want_traj = j.x || j.y || j.kx || j.ky;
+    const bool shared_queue = q.devices > 1;
     WorkArea &w = d.work;
     DevBuf buf[2];
     int nbuf = 1;
-    int64_t chunk = n;
+    int64_t chunk = n, taken = 0;
+    int slabs = 0;
     {
         cudaError_t e = cudaSetDevice(d.dev);
         if (e != cudaSuccess) return bail(MR_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
@@ -563,16 +593,28 @@ static int trace_block_on_device(DeviceFields &d, const HostJob &j, int64_t lo, 
         // bytes one ray needs on the device
         const double env_row = (j.env.depth ? 4.0 : 0.0) + (j.env.u ? 8.0 : 0.0) + (j.env.v ? 8.0 : 0.0);
         const double per_ray = 32.0 + (want_traj ? (32.0 + env_row) * (double)j.rows_cap : 0.0) + 8.0 + 32.0;
-        double budget = 0.80 * (double)(free_b + w.held());      // what this handle already holds is ours to reuse
+        const double budget = 0.80 * (double)(free_b + w.held());      // what this handle already holds is ours to reuse
+        const int64_t wave = 148 * 4 * kBlock;              // rays that fill the machine once
         if (j.o.chunk_rays > 0) {
             chunk = std::min<int64_t>(n, j.o.chunk_rays);
-        } else if (per_ray * (double)n > budget || (want_traj && per_ray * (double)n > 4e9)) {
-            // does not fit, or is big enough that overlapping the drain with the next
-            // slab's integration pays: two slabs in flight
-            const double cap = std::min(budget / 2.0, 16e9);
-            const int64_t wave = 148 * 4 * kBlock;          // rays that fill the machine once
-            chunk = (int64_t)(cap / per_ray);
-            if (chunk >= wave) chunk = chunk / wave * wave;
+        } else {
+            if (per_ray * (double)n > budget || (want_traj && per_ray * (double)n > 4e9)) {
+                // does not fit, or is big enough that overlapping the drain with the next
+                // slab's integration pays: two slabs in flight
+                const double cap = std::min(budget / 2.0, 16e9);
+                chunk = (int64_t)(cap / per_ray);
+                if (chunk >= wave) chunk = chunk / wave * wave;
+            }
+            if (shared_queue) {
+                // several devices on one queue: about sixteen slabs per device, so that the last slab a device
+                // takes is a small share of its work — but a slab fills the machine (7 blocks on each of 148 SMs)
+                // unless the batch is too small to give every device that much
+                const int64_t G = q.devices, full = 148 * 7 * kBlock;
+                const int64_t per_dev = (n + G - 1) / G, target = (n + G * 16 - 1) / (G * 16);
+                int64_t want = std::max(target, std::min(full, per_dev));
+                want = (want + kBlock - 1) / kBlock * kBlock;
+                chunk = std::min(chunk, want);
+            }
             chunk = std::max<int64_t>(std::min(chunk, n), 1);
         }
         nbuf = chunk < n ? 2 : 1;
@@ -605,11 +647,25 @@ static int trace_block_on_device(DeviceFields &d, const HostJob &j, int64_t lo, 
     t_alloc = clk::now();
     {
         cudaStream_t s_comp = w.s_comp, s_copy = w.s_copy;
-        int k = 0;
-        for (int64_t c0 = lo; c0 < hi; c0 += chunk, ++k) {
+        const size_t max_pitch = d.max_pitch;
+        for (int k = 0;; ++k) {
             DevBuf &B = buf[k % nbuf];
-            const int64_t m = std::min(chunk, hi - c0);
-            if (k >= nbuf) MR_TRY(cudaStreamWaitEvent(s_comp, B.drained, 0));
+            if (shared_queue) {
+                // With other devices on the queue a slab is taken only when this device can start on it: the
+                // previous slab has been integrated (it may still be draining) and this buffer's previous slab has
+                // left it.  That is what balances the devices; the gap it leaves between two kernels is a launch
+                // latency against tens of milliseconds of integration.
+                if (k >= 1) MR_TRY(cudaEventSynchronize(buf[(k - 1) % nbuf].computed));
+                if (k >= nbuf) MR_TRY(cudaEventSynchronize(B.drained));
+            } else if (k >= nbuf) {
+                // alone on the queue the host runs ahead and the compute stream waits for the buffer
+                MR_TRY(cudaStreamWaitEvent(s_comp, B.drained, 0));
+            }
+            if (q.failed.load()) break;
+            const int64_t c0 = q.next.fetch_add(chunk);
+            if (c0 >= n) break;
+            const int64_t m = std::min(chunk, n - c0);
+            taken += m; ++slabs;
             MR_TRY(cudaMemcpyAsync(B.ic,             j.x0  + c0, sizeof(double) * m, cudaMemcpyHostToDevice, s_comp));
             MR_TRY(cudaMemcpyAsync(B.ic + chunk,     j.y0  + c0, sizeof(double) * m, cudaMemcpyHostToDevice, s_comp));
             MR_TRY(cudaMemcpyAsync(B.ic + 2 * chunk, j.kx0 + c0, sizeof(double) * m, cudaMemcpyHostToDevice, s_comp));
@@ -625,6 +681,7 @@ static int trace_block_on_device(DeviceFields &d, const HostJob &j, int64_t lo, 
                 a.ld = chunk;
                 a.rows = B.rows; a.len = B.len; a.fin = B.fin;
                 a.deep_map = want_deep_map(d, j.o);
+                a.same_grid = !(j.o.flags & MR_OPT_NO_SAME_GRID);
                 // fin is [4][n] with n = m for the kernel (it uses a.n as the pitch)
                 cudaError_t e = j.o.math == MR_MATH_STRICT ? launch_trace_strict(a, s_comp) : launch_trace_fast(a, s_comp);
                 if (e != cudaSuccess) { rc = bail(MR_ERR_CUDA, std::string("trace kernel launch: ") + cudaGetErrorString(e)); goto done; }
@@ -633,23 +690,19 @@ static int trace_block_on_device(DeviceFields &d, const HostJob &j, int64_t lo, 
                 MR_TRY(launch_sample(d.b, d.c, j.rows_cap, m, chunk, tx, tx + plane, B.depth, B.u, B.v, s_comp));
             MR_TRY(cudaEventRecord(B.computed, s_comp));
             MR_TRY(cudaStreamWaitEvent(s_copy, B.computed, 0));
+            const size_t rows_cap = (size_t)j.rows_cap, nt = (size_t)j.n_total, ch = (size_t)chunk, mm = (size_t)m;
             if (j.env.depth)
-                MR_TRY(cudaMemcpy2DAsync(j.env.depth + c0, sizeof(float) * (size_t)j.n_total, B.depth, sizeof(float) * (size_t)chunk,
-                                         sizeof(float) * (size_t)m, (size_t)j.rows_cap, cudaMemcpyDeviceToHost, s_copy));
+                MR_TRY(copy_columns_d2h(j.env.depth + c0, sizeof(float) * nt, B.depth, sizeof(float) * ch, sizeof(float) * mm, rows_cap, max_pitch, s_copy));
             if (j.env.u)
-                MR_TRY(cudaMemcpy2DAsync(j.env.u + c0, sizeof(double) * (size_t)j.n_total, B.u, sizeof(double) * (size_t)chunk,
-                                         sizeof(double) * (size_t)m, (size_t)j.rows_cap, cudaMemcpyDeviceToHost, s_copy));
+                MR_TRY(copy_columns_d2h(j.env.u + c0, sizeof(double) * nt, B.u, sizeof(double) * ch, sizeof(double) * mm, rows_cap, max_pitch, s_copy));
             if (j.env.v)
-                MR_TRY(cudaMemcpy2DAsync(j.env.v + c0, sizeof(double) * (size_t)j.n_total, B.v, sizeof(double) * (size_t)chunk,
-                                         sizeof(double) * (size_t)m, (size_t)j.rows_cap, cudaMemcpyDeviceToHost, s_copy));
+                MR_TRY(copy_columns_d2h(j.env.v + c0, sizeof(double) * nt, B.v, sizeof(double) * ch, sizeof(double) * mm, rows_cap, max_pitch, s_copy));
             if (want_traj) {
                 double *dsts[4] = { j.x, j.y, j.kx, j.ky };
                 for (int f = 0; f < 4; ++f) {
                     if (!dsts[f]) continue;
-                    MR_TRY(cudaMemcpy2DAsync(dsts[f] + c0, sizeof(double) * (size_t)j.n_total,
-                                             B.traj + f * plane, sizeof(double) * (size_t)chunk,
-                                             sizeof(double) * (size_t)m, (size_t)j.rows_cap,
-                                             cudaMemcpyDeviceToHost, s_copy));
+                    MR_TRY(copy_columns_d2h(dsts[f] + c0, sizeof(double) * nt, B.traj + f * plane, sizeof(double) * ch,
+                                            sizeof(double) * mm, rows_cap, max_pitch, s_copy));
                 }
             }
             if (j.rows) MR_TRY(cudaMemcpyAsync(j.rows + c0, B.rows, sizeof(int32_t) * m, cudaMemcpyDeviceToHost, s_copy));
@@ -675,13 +728,54 @@ done:
     }
     if (timing) {
         auto ms = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
-        std::fprintf(stderr, "[mantaray_b200] device %d: %lld rays in slabs of %lld (%d buffers): alloc %.1f ms, enqueue %.1f ms, "
-                             "drain %.1f ms, tail %.1f ms, %.2f GB held\n", d.dev, (long long)n, (long long)chunk, nbuf,
+        std::fprintf(stderr, "[mantaray_b200] device %d: %lld of %lld rays in %d slabs of %lld (%d buffers): alloc %.1f ms, enqueue %.1f ms, "
+                             "drain %.1f ms, tail %.1f ms, %.2f GB held\n", d.dev, (long long)taken, (long long)n, slabs, (long long)chunk, nbuf,
                      ms(t_begin, t_alloc), ms(t_alloc, t_enqueued), ms(t_enqueued, t_synced), ms(t_synced, clk::now()),
                      (double)w.held() / 1e9);
     }
+    d.last_taken = taken;
     return rc;
 #undef MR_TRY
+}
+
+// The whole batch on the handle's devices: one worker thread per device on a shared slab queue.
+static int run_host_job(mr_fields *f, const HostJob &j, int max_devices)
+{
+    const int G = std::max(1, std::min((int)f->devs.size(), max_devices));
+    SlabQueue q;
+    q.n = j.n_total; q.devices = G;
+    std::vector<int> rcs((size_t)G, MR_OK);
+    std::vector<std::string> errs((size_t)G);
+    for (auto &d : f->devs) d.last_taken = 0;
+    if (G == 1) {
+        rcs[0] = trace_slabs_on_device(f->devs[0], j, q, errs[0]);
+    } else {
+        std::vector<std::thread> th;
+        th.reserve((size_t)G);
+        auto worker = [&](int g) {
+            try {
+                rcs[(size_t)g] = trace_slabs_on_device(f->devs[(size_t)g], j, q, errs[(size_t)g]);
+            } catch (...) {                 // nothing may leave a thread: it would be std::terminate
+                rcs[(size_t)g] = translate_exception("device worker");
+                try { errs[(size_t)g] = g_err; } catch (...) {}
+                q.failed.store(true);
+            }
+        };
+        int started = 0;
+        try {
+            for (int g = 1; g < G; ++g) { th.emplace_back(worker, g); ++started; }
+        } catch (...) {
+            // a thread could not be created: the devices that did start (and this thread) share the queue
+            translate_exception("mr_trace_many");
+        }
+        (void)started;
+        worker(0);                          // the calling thread drives the first device
+        for (auto &t_ : th) t_.join();
+    }
+    for (int g = 0; g < G; ++g)
+        if (rcs[(size_t)g] != MR_OK) return fail(rcs[(size_t)g], "device " + std::to_string(f->devs[(size_t)g].dev) + ": " + errs[(size_t)g]);
+    if (q.next.load() < j.n_total) return fail(MR_ERR_CUDA, "mr_trace_many: the slab queue was abandoned before the last ray");
+    return MR_OK;
 }
 
 }  // namespace mr
@@ -700,6 +794,7 @@ const char *mr_last_error(void) { return g_err.c_str(); }
 int mr_fields_create(const mr_bathymetry_desc *bathy, const mr_current_desc *current,
                      uint32_t device_mask, mr_fields **out)
 {
+    MR_API_BEGIN
     if (!out) return fail(MR_ERR_BAD_ARG, "mr_fields_create: out is NULL");
     *out = nullptr;
     int rc = validate(bathy, current);
@@ -726,11 +821,13 @@ int mr_fields_create(const mr_bathymetry_desc *bathy, const mr_current_desc *cur
     }
     *out = f.release();
     return MR_OK;
+    MR_API_END("mr_fields_create")
 }
 
 int mr_fields_open_netcdf3(const char *bathymetry_path, const char *current_path,
                            uint32_t device_mask, mr_fields **out)
 {
+    MR_API_BEGIN
     if (!out) return fail(MR_ERR_BAD_ARG, "mr_fields_open_netcdf3: out is NULL");
     *out = nullptr;
     std::string err;
@@ -773,6 +870,7 @@ int mr_fields_open_netcdf3(const char *bathymetry_path, const char *current_path
         c.kind = MR_CURRENT_CONSTANT; c.u0 = 0.0; c.v0 = 0.0;  // DEFAULT_CURRENT constant_current.rs:10
     }
     return mr_fields_create(&b, &c, device_mask, out);
+    MR_API_END("mr_fields_open_netcdf3")
 }
 
 void mr_fields_free(mr_fields *f)
@@ -783,6 +881,15 @@ void mr_fields_free(mr_fields *f)
 }
 
 uint32_t mr_fields_device_mask(const mr_fields *f) { return f ? f->mask : 0; }
+
+int mr_fields_last_split(mr_fields *f, int64_t *rays_per_device, int32_t cap)
+{
+    if (!f || (cap > 0 && !rays_per_device)) return fail(MR_ERR_BAD_ARG, "mr_fields_last_split: NULL argument");
+    std::lock_guard<std::mutex> guard(f->mu);
+    const int n = (int)f->devs.size();
+    for (int g = 0; g < n && g < cap; ++g) rays_per_device[g] = f->devs[(size_t)g].last_taken;
+    return n;
+}
 
 void mr_fields_trim(mr_fields *f)
 {
@@ -795,7 +902,8 @@ int64_t mr_num_steps(double t0, double t_end, double dt)
 {
     if (!(dt > 0.0)) return -1;
     double q = std::ceil((t_end - t0) / dt);
-    if (!(q >= 0.0) || !(q < 2147483646.0)) return -1;
+    if (std::isnan(q) || !(q < 2147483646.0)) return -1;
+    if (q < 0.0) return 0;             // `((x_end - x) / h).ceil() as usize` saturates a negative quotient to 0 steps
     return (int64_t)q;
 }
 
@@ -833,6 +941,7 @@ int mr_trace_many_env(mr_fields *f, int64_t n,
                       double *t, double *x, double *y, double *kx, double *ky,
                       int32_t *rows, int32_t *len, double *final_state, const mr_env_planes *env)
 {
+    MR_API_BEGIN
     if (!f) return fail(MR_ERR_BAD_ARG, "mr_trace_many: NULL field handle");
     if (n < 0) return fail(MR_ERR_BAD_ARG, "mr_trace_many: n < 0");
     if (n > 0 && (!x0 || !y0 || !kx0 || !ky0)) return fail(MR_ERR_BAD_ARG, "mr_trace_many: NULL initial-condition array");
@@ -840,7 +949,7 @@ int mr_trace_many_env(mr_fields *f, int64_t n,
     normalise_opts(opts, o);
     if (o.math != MR_MATH_FAST && o.math != MR_MATH_STRICT) return fail(MR_ERR_BAD_ARG, "mr_trace_opts.math must be MR_MATH_FAST or MR_MATH_STRICT");
     const int64_t nsteps = mr_num_steps(t0, t_end, dt);
-    if (nsteps < 0) return fail(MR_ERR_BAD_ARG, "mr_trace_many: need dt > 0 and 0 <= (t_end - t0)/dt < 2^31 (the reference panics here)");
+    if (nsteps < 0) return fail(MR_ERR_BAD_ARG, "mr_trace_many: need dt > 0 and a finite (t_end - t0)/dt < 2^31");
     const bool any_traj = x || y || kx || ky;
     if (any_traj && !(x && y && kx && ky)) return fail(MR_ERR_BAD_ARG, "mr_trace_many: pass all four of x, y, kx, ky or none");
     const bool any_env = env && (env->depth || env->u || env->v);
@@ -855,37 +964,21 @@ int mr_trace_many_env(mr_fields *f, int64_t n,
     j.env = any_env ? *env : mr_env_planes{nullptr, nullptr, nullptr};
 
     std::lock_guard<std::mutex> guard(f->mu);
-    const int G = (int)f->devs.size();
-    // contiguous blocks of rays per device, rounded to whole thread blocks
-    int64_t per = (n + G - 1) / G;
-    per = (per + kBlock - 1) / kBlock * kBlock;
-    std::vector<int> rcs(G, MR_OK);
-    std::vector<std::string> errs(G);
-    if (G == 1) {
-        rcs[0] = trace_block_on_device(f->devs[0], j, 0, n, errs[0]);
-    } else {
-        std::vector<std::thread> th;
-        for (int g = 0; g < G; ++g) {
-            int64_t lo = std::min<int64_t>((int64_t)g * per, n), hi = std::min<int64_t>(lo + per, n);
-            th.emplace_back([&, g, lo, hi] { rcs[g] = trace_block_on_device(f->devs[g], j, lo, hi, errs[g]); });
-        }
-        for (auto &t_ : th) t_.join();
-    }
-    for (int g = 0; g < G; ++g)
-        if (rcs[g] != MR_OK) return fail(rcs[g], "device " + std::to_string(f->devs[g].dev) + ": " + errs[g]);
-    return MR_OK;
+    return run_host_job(f, j, (int)f->devs.size());
+    MR_API_END("mr_trace_many")
 }
 
 int mr_single_ray(mr_fields *f, double x0, double y0, double kx0, double ky0,
                   double t0, double t_end, double dt, const mr_trace_opts *opts,
                   double *out, int64_t out_cap, int64_t *n_rows)
 {
+    MR_API_BEGIN
     if (!f || !n_rows) return fail(MR_ERR_BAD_ARG, "mr_single_ray: NULL argument");
     mr_trace_opts o;
     normalise_opts(opts, o);
     if (o.stride != 1) return fail(MR_ERR_BAD_ARG, "mr_single_ray: stride must be 1");
     const int64_t nsteps = mr_num_steps(t0, t_end, dt);
-    if (nsteps < 0) return fail(MR_ERR_BAD_ARG, "mr_single_ray: need dt > 0 and 0 <= (t_end - t0)/dt < 2^31 (the reference panics here)");
+    if (nsteps < 0) return fail(MR_ERR_BAD_ARG, "mr_single_ray: need dt > 0 and a finite (t_end - t0)/dt < 2^31");
     const int64_t cap = nsteps + 1;
     std::vector<double> t((size_t)cap), soa((size_t)cap * 4);
     int32_t rows = 0;
@@ -899,9 +992,8 @@ int mr_single_ray(mr_fields *f, double x0, double y0, double kx0, double ky0,
     j.env = mr_env_planes{nullptr, nullptr, nullptr};
     {
         std::lock_guard<std::mutex> guard(f->mu);
-        std::string err;
-        int rc = trace_block_on_device(f->devs[0], j, 0, 1, err);
-        if (rc) return fail(rc, "device " + std::to_string(f->devs[0].dev) + ": " + err);
+        int rc = run_host_job(f, j, 1);
+        if (rc) return rc;
     }
     *n_rows = rows;
     if (rows > out_cap || !out) return fail(MR_ERR_BAD_ARG, "mr_single_ray: out holds " + std::to_string(out_cap) +
@@ -911,6 +1003,7 @@ int mr_single_ray(mr_fields *f, double x0, double y0, double kx0, double ky0,
         for (int c = 0; c < 4; ++c) out[5 * r + 1 + c] = soa[(size_t)c * cap + r];
     }
     return MR_OK;
+    MR_API_END("mr_single_ray")
 }
 
 int mr_trace_device(mr_fields *f, int device, void *stream, int64_t n,
@@ -919,6 +1012,7 @@ int mr_trace_device(mr_fields *f, int device, void *stream, int64_t n,
                     double *d_x, double *d_y, double *d_kx, double *d_ky, int64_t ld,
                     int32_t *d_rows, int32_t *d_len, double *d_final, int32_t *launches)
 {
+    MR_API_BEGIN
     if (launches) *launches = 0;
     if (!f) return fail(MR_ERR_BAD_ARG, "mr_trace_device: NULL field handle");
     const DeviceFields *d = find_device(f, device);
@@ -928,7 +1022,7 @@ int mr_trace_device(mr_fields *f, int device, void *stream, int64_t n,
     mr_trace_opts o;
     normalise_opts(opts, o);
     const int64_t nsteps = mr_num_steps(t0, t_end, dt);
-    if (nsteps < 0) return fail(MR_ERR_BAD_ARG, "mr_trace_device: need dt > 0 and 0 <= (t_end - t0)/dt < 2^31");
+    if (nsteps < 0) return fail(MR_ERR_BAD_ARG, "mr_trace_device: need dt > 0 and a finite (t_end - t0)/dt < 2^31");
     const bool any_traj = d_x || d_y || d_kx || d_ky;
     if (any_traj && !(d_x && d_y && d_kx && d_ky)) return fail(MR_ERR_BAD_ARG, "mr_trace_device: pass all four of x, y, kx, ky or none");
     if (any_traj && ld < n) return fail(MR_ERR_BAD_ARG, "mr_trace_device: ld < n");
@@ -941,12 +1035,14 @@ int mr_trace_device(mr_fields *f, int device, void *stream, int64_t n,
     if (cur != device) cudaSetDevice(cur);
     if (rc == MR_OK && launches) *launches = 1;
     return rc;
+    MR_API_END("mr_trace_device")
 }
 
 int mr_sample_device(mr_fields *f, int device, void *stream, int64_t rows, int64_t n, int64_t ld,
                      const double *d_x, const double *d_y,
                      float *d_depth, double *d_u, double *d_v, int32_t *launches)
 {
+    MR_API_BEGIN
     if (launches) *launches = 0;
     if (!f) return fail(MR_ERR_BAD_ARG, "mr_sample_device: NULL field handle");
     const DeviceFields *d = find_device(f, device);
@@ -962,11 +1058,13 @@ int mr_sample_device(mr_fields *f, int device, void *stream, int64_t rows, int64
     if (e != cudaSuccess) return fail(MR_ERR_CUDA, std::string("sample kernel launch: ") + cudaGetErrorString(e));
     if (launches) *launches = 1;
     return MR_OK;
+    MR_API_END("mr_sample_device")
 }
 
 int mr_sample_fields(mr_fields *f, int64_t count, const double *x, const double *y,
                      float *depth, double *u, double *v)
 {
+    MR_API_BEGIN
     if (!f) return fail(MR_ERR_BAD_ARG, "mr_sample_fields: NULL field handle");
     if (count < 0) return fail(MR_ERR_BAD_ARG, "mr_sample_fields: count < 0");
     if (count == 0 || !(depth || u || v)) return MR_OK;
@@ -1009,55 +1107,13 @@ int mr_sample_fields(mr_fields *f, int64_t count, const double *x, const double 
 #undef MR_TRY
     release();
     return MR_OK;
-}
-
-int mr_measure_fp64_peak(int device, int millis, double *tflops)
-{
-    if (!tflops) return fail(MR_ERR_BAD_ARG, "mr_measure_fp64_peak: NULL output");
-    *tflops = 0.0;
-    if (device < 0 || device >= device_count_quiet()) return fail(MR_ERR_CUDA, "mr_measure_fp64_peak: no such CUDA device");
-    int cur = -1;
-    MR_CUDA(cudaGetDevice(&cur));
-    MR_CUDA(cudaSetDevice(device));
-    cudaDeviceProp prop;
-    MR_CUDA(cudaGetDeviceProperties(&prop, device));
-    double *sink = nullptr;
-    MR_CUDA(cudaMalloc(&sink, sizeof(double)));
-    cudaEvent_t e0, e1;
-    MR_CUDA(cudaEventCreate(&e0));
-    MR_CUDA(cudaEventCreate(&e1));
-    const int blocks = prop.multiProcessorCount * 8;
-    int iters = 2000;
-    double best = 0.0;
-    float ms = 0.f;
-    // warm up, then size the loop for ~millis of work
-    MR_CUDA(launch_dfma_probe(sink, iters, blocks, 0));
-    MR_CUDA(cudaDeviceSynchronize());
-    for (int rep = 0; rep < 4; ++rep) {
-        MR_CUDA(cudaEventRecord(e0, 0));
-        MR_CUDA(launch_dfma_probe(sink, iters, blocks, 0));
-        MR_CUDA(cudaEventRecord(e1, 0));
-        MR_CUDA(cudaEventSynchronize(e1));
-        MR_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-        double flops = 2.0 * 64.0 * (double)iters * 256.0 * (double)blocks;
-        double tf = flops / ((double)ms * 1e-3) / 1e12;
-        if (rep > 0) best = std::max(best, tf);
-        if (rep == 0 && ms > 0.f && millis > 0) {
-            double scale = (double)millis / ms;
-            iters = (int)std::min(2e6, std::max(200.0, iters * scale));
-        }
-    }
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    cudaFree(sink);
-    if (cur != device) cudaSetDevice(cur);
-    *tflops = best;
-    return MR_OK;
+    MR_API_END("mr_sample_fields")
 }
 
 int mr_depth_floor_map(const mr_bathymetry_desc *b, float *out, size_t cap, int32_t *nbx, int32_t *nby, float *deep_frac,
                        int32_t *affine)
 {
+    MR_API_BEGIN
     if (!b || !nbx || !nby) return fail(MR_ERR_BAD_ARG, "mr_depth_floor_map: NULL argument");
     if (b->kind != MR_BATHY_GRID || b->nx < 2 || b->ny < 2 || !b->depth || !b->x || !b->y)
         return fail(MR_ERR_BAD_ARG, "mr_depth_floor_map: needs a GRID bathymetry with nx, ny >= 2");
@@ -1076,34 +1132,13 @@ int mr_depth_floor_map(const mr_bathymetry_desc *b, float *out, size_t cap, int3
         std::memcpy(out, m.data(), m.size() * sizeof(float));
     }
     return MR_OK;
-}
-
-int mr_selftest_fdiv(int device, float spacing, uint64_t *mismatches, int32_t *usable)
-{
-    if (!mismatches || !usable) return fail(MR_ERR_BAD_ARG, "mr_selftest_fdiv: NULL output");
-    *mismatches = 0;
-    float r = 0.f;
-    *usable = recip_ok(spacing, &r) ? 1 : 0;
-    if (!*usable) return MR_OK;
-    if (device < 0 || device >= device_count_quiet()) return fail(MR_ERR_CUDA, "mr_selftest_fdiv: no such CUDA device");
-    int cur = -1;
-    MR_CUDA(cudaGetDevice(&cur));
-    MR_CUDA(cudaSetDevice(device));
-    unsigned long long *bad = nullptr, h = 0;
-    MR_CUDA(cudaMalloc(&bad, sizeof(*bad)));
-    MR_CUDA(cudaMemset(bad, 0, sizeof(*bad)));
-    fdiv_selftest_kernel<<<148 * 32, 256>>>(spacing, r, bad);
-    MR_CUDA(cudaGetLastError());
-    MR_CUDA(cudaMemcpy(&h, bad, sizeof(h), cudaMemcpyDeviceToHost));
-    cudaFree(bad);
-    if (cur != device) cudaSetDevice(cur);
-    *mismatches = h;
-    return MR_OK;
+    MR_API_END("mr_depth_floor_map")
 }
 
 // ---- NetCDF-3 ---------------------------------------------------------------
 int mr_nc3_open(const char *path, mr_nc3 **out)
 {
+    MR_API_BEGIN
     if (!path || !out) return fail(MR_ERR_BAD_ARG, "mr_nc3_open: NULL argument");
     *out = nullptr;
     std::unique_ptr<mr_nc3> h(new (std::nothrow) mr_nc3);
@@ -1113,18 +1148,22 @@ int mr_nc3_open(const char *path, mr_nc3 **out)
     if (rc) return fail(rc, err);
     *out = h.release();
     return MR_OK;
+    MR_API_END("mr_nc3_open")
 }
 void mr_nc3_close(mr_nc3 *f) { delete f; }
 int mr_nc3_var_count(const mr_nc3 *f) { return f ? (int)f->file.vars.size() : 0; }
 int mr_nc3_var_name(const mr_nc3 *f, int index, char *buf, size_t cap)
 {
+    MR_API_BEGIN
     if (!f || !buf || cap == 0 || index < 0 || index >= (int)f->file.vars.size()) return fail(MR_ERR_BAD_ARG, "mr_nc3_var_name: bad argument");
     std::strncpy(buf, f->file.vars[(size_t)index].name.c_str(), cap - 1);
     buf[cap - 1] = 0;
     return MR_OK;
+    MR_API_END("mr_nc3_var_name")
 }
 int mr_nc3_var_info(const mr_nc3 *f, const char *name, int32_t *nc_type, int64_t *n_elems, int32_t *ndims, int64_t dims[MR_NC3_MAX_DIMS])
 {
+    MR_API_BEGIN
     if (!f || !name) return fail(MR_ERR_BAD_ARG, "mr_nc3_var_info: NULL argument");
     const Nc3Var *v = f->file.find(name);
     if (!v) return fail(MR_ERR_FORMAT, "'" + f->file.path + "': no variable named '" + name + "'");
@@ -1137,9 +1176,11 @@ int mr_nc3_var_info(const mr_nc3 *f, const char *name, int32_t *nc_type, int64_t
             dims[k] = (k == 0 && v->is_record) ? (int64_t)f->file.numrecs : (int64_t)l;
         }
     return MR_OK;
+    MR_API_END("mr_nc3_var_info")
 }
 int mr_nc3_read_f32(const mr_nc3 *f, const char *name, float *out, int64_t cap)
 {
+    MR_API_BEGIN
     if (!f || !name || !out) return fail(MR_ERR_BAD_ARG, "mr_nc3_read_f32: NULL argument");
     std::vector<float> v;
     std::string err;
@@ -1148,9 +1189,11 @@ int mr_nc3_read_f32(const mr_nc3 *f, const char *name, float *out, int64_t cap)
     if ((int64_t)v.size() > cap) return fail(MR_ERR_BAD_ARG, "mr_nc3_read_f32: buffer too small");
     std::memcpy(out, v.data(), v.size() * sizeof(float));
     return MR_OK;
+    MR_API_END("mr_nc3_read_f32")
 }
 int mr_nc3_read_f64(const mr_nc3 *f, const char *name, double *out, int64_t cap)
 {
+    MR_API_BEGIN
     if (!f || !name || !out) return fail(MR_ERR_BAD_ARG, "mr_nc3_read_f64: NULL argument");
     std::vector<double> v;
     std::string err;
@@ -1159,6 +1202,7 @@ int mr_nc3_read_f64(const mr_nc3 *f, const char *name, double *out, int64_t cap)
     if ((int64_t)v.size() > cap) return fail(MR_ERR_BAD_ARG, "mr_nc3_read_f64: buffer too small");
     std::memcpy(out, v.data(), v.size() * sizeof(double));
     return MR_OK;
+    MR_API_END("mr_nc3_read_f64")
 }
 
 // ---- pinned host memory -------------------------------------------------------

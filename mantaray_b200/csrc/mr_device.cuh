@@ -29,6 +29,28 @@
 
 namespace mr {
 
+// experiment knob: with the same-grid shortcut, hand the current's cell geometry to the bathymetry lookup
+// (saves ~14 instructions per shallow evaluation, costs the registers that keep it alive)
+// experiment knob: deep lanes of the depth-floor map take the fourth-root form (no k, no direction cosines)
+#ifndef MR_DEEP_ROOT4
+#define MR_DEEP_ROOT4 1
+#endif
+// experiment knob: fold the current's four gradients into the two advection sums -kx du/dx - ky dv/dx and
+// -kx du/dy - ky dv/dy as soon as the record is there (they need nothing but the wavenumber), so that eight
+// registers are not held through the bilinears and the wave terms
+// experiment knob: with the depth-floor map, the lanes that are NOT proven deep fetch their bathymetry record only
+// when they reach the depth lookup (one more exposed round trip for those lanes) instead of with the other loads
+// (eight registers reserved through the current's bilinear in every lane)
+#ifndef MR_DMAP_LATE_LOAD
+#define MR_DMAP_LATE_LOAD 1
+#endif
+#ifndef MR_EARLY_GRAD
+#define MR_EARLY_GRAD 1
+#endif
+#ifndef MR_SG_SHARE_GEOM
+#define MR_SG_SHARE_GEOM 1
+#endif
+
 typedef unsigned long long f32x2;    // two f32 in one 64-bit register (lo, hi), see the packed helpers below
 
 // ---- device-resident field descriptors (passed by value as kernel params) ----
@@ -63,6 +85,12 @@ struct BathyDev {
     // non-finite node); [dmap_nby][dmap_nbx] floats, row-major
     const float *dmap;
     int32_t dmap_nbx;
+    // Same-grid shortcut (FastRay, SG): the current lives on this very grid — same shape, same f32 coordinates,
+    // and f64 coordinates that are exactly the f32 ones widened.  Then the current's cell (from its f64 index,
+    // cartesian_current.rs:246) is the bathymetry's cell (from the f32 index, cartesian_netcdf3.rs:289) whenever
+    // the f32 index is further than sg_delta from an integer; sg_lim = 0.5 - sg_delta.  0: not applicable.
+    int32_t same_grid;
+    float sg_lim;
 };
 static constexpr int kDeepShift = 3;                 // log2 of the block side, in cells
 static constexpr int kDeepBlock = 1 << kDeepShift;
@@ -98,10 +126,11 @@ static __constant__ double kExpm1C[12] = {
     1.6059043836821613e-10, 2.08767569878681e-09, 2.505210838544172e-08, 2.755731922398589e-07,
     2.7557319223985893e-06, 2.48015873015873e-05, 1.984126984126984e-04, 1.388888888888889e-03,
     8.333333333333333e-03, 4.1666666666666664e-02, 1.6666666666666666e-01, 0.5};
-// {log2(e), 1.5*2^52, ln2_hi, ln2_lo, deep-water threshold on kh, G, G/2}
-static __constant__ double kExpRed[7] = {1.4426950408889634074, 6755399441055744.0,
+// {log2(e), 1.5*2^52, ln2_hi, ln2_lo, deep-water threshold on kh, G, G/2, sqrt(G)/2}
+static __constant__ double kExpRed[8] = {1.4426950408889634074, 6755399441055744.0,
                                          6.93147180369123816490e-01, 1.90821492927058770002e-10,
-                                         22.0, 9.8, 4.9};
+                                         22.0, 9.8, 4.9,
+                                         1.5652475842498528};      // sqrt(G) / 2: deep-water cg = (sqrt(G)/2) k^-1/2
 
 __device__ __forceinline__ double qnan() { return __longlong_as_double(0x7ff8000000000000LL); }
 __device__ __forceinline__ float  qnanf() { return __int_as_float(0x7fc00000); }
@@ -442,6 +471,24 @@ __device__ __forceinline__ double recip(double x)
     return fma(r0, e, r0);
 }
 
+// x^(-1/4) for a normal, positive, finite x: three MUFU seeds (x^-1/2, its own inverse square root x^1/4, the
+// reciprocal of that: ~2^-20 together) and two Newton steps t += t (1 - x t^4) / 4 (error e -> 2.5 e^2) -> ~2 ulp.
+// x = +inf gives NaN (0 * inf in the residual), NaN gives NaN.
+__device__ __forceinline__ double inv_root4(double x)
+{
+    double y, s, t;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(s) : "d"(y));
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(t) : "d"(s));
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const double t2 = t * t;
+        const double e = fma(-x, t2 * t2, 1.0);
+        t = fma(0.25 * t, e, t);
+    }
+    return t;
+}
+
 // E = exp(z) and em = expm1(z) for z in [-44, 0] (larger kh takes the deep-water branch).
 // z = n ln2 + r, |r| <= ln2/2;  expm1(r) = r + r^2 P(r) (Taylor through r^13, remainder
 // < 2e-17 relative);  E = 2^n (1 + p),  em = 2^n p + (2^n - 1)  (2^n - 1 is exact).
@@ -508,34 +555,6 @@ __device__ __forceinline__ void wave_terms(double k, double h, double dhdx, doub
         bx = -zk * dhdx; by = -zk * dhdy;
     }
 }
-// The same for a point already known to lie in deep water over finite, positive depths (depth-floor map):
-// the deep-water branch above with h and grad(h) finite, i.e. z = zk and -zk * grad(h) = -zk up to the
-// sign of an exact zero.  k NaN (k^2 infinite) still turns everything NaN.
-__device__ __forceinline__ void wave_terms_deep(double k, double &cg, double &bx, double &by)
-{
-    const double zk = k * 0.0;
-    double sq, rq;
-    sqrt_rsqrt(k * kExpRed[5], sq, rq);
-    cg = fma(kExpRed[6], rq, zk);
-    bx = -zk; by = -zk;
-}
-__device__ __forceinline__ void assemble_rhs(double kx, double ky, double cs, double sn, double cg, double bx, double by,
-                                             const CurrentVal &cv, double out[4])
-{
-    out[0] = fma(cg, cs, cv.u);
-    out[1] = fma(cg, sn, cv.v);
-    out[2] = fma(-ky, cv.dvdx, fma(-kx, cv.dudx, bx));
-    out[3] = fma(-ky, cv.dvdy, fma(-kx, cv.dudy, by));
-}
-__device__ __forceinline__ void rhs_f64_fast(double kx, double ky, double k, double cs, double sn,
-                                             double h, double dhdx, double dhdy,
-                                             const CurrentVal &cv, double out[4])
-{
-    double cg, bx, by;
-    wave_terms(k, h, dhdx, dhdy, cg, bx, by);
-    assemble_rhs(kx, ky, cs, sn, cg, bx, by, cv, out);
-}
-
 // =============================================================================
 // the fast RHS, in four phases so that every load of an evaluation is in flight
 // before anything waits on one:
@@ -560,9 +579,21 @@ __device__ __forceinline__ void rhs_f64_fast(double kx, double ky, double k, dou
 // without the cell record: no 32-byte sector fetched (the map's floats are shared by whole blocks of lanes),
 // no bilinear, no corner test.  Lanes that fail the test — shallow water, a dry or non-finite node in the
 // block, a failed lookup — load the record and proceed exactly as without the map.
-template <int BK, int CK, bool UNI, bool DMAP = false>
+// SG (both fields gridded, affine, on the SAME grid; BathyDev::same_grid): one f32 fractional index serves both
+// fields.  The reference computes two — f32 for the bathymetry (cartesian_netcdf3.rs:289), f64 for the current
+// (cartesian_current.rs:246) — and they can name different cells only when the position is within a rounding
+// error of a grid line: |ix32 - I| <= 2^-24 (3 n + |x0|/s) and |ix64 - I| <= 2^-51 n around the exact index I.
+// So when the f32 index lies further than sg_delta (that bound plus slack) from every integer, both floors are
+// equal and both bounds tests pass, and neither the f64 index nor any bounds test is evaluated; the cell
+// geometry (corner coordinates, in-cell fractions, the corner-coincidence test of interpolator.rs:46-50) is then
+// shared too.  Within sg_delta of a grid line (< 0.2 % of evaluations per axis on a 2048-point axis) the lane takes
+// the two separate lookups exactly as without SG.  Every value is the one the separate lookups produce.
+template <int BK, int CK, bool UNI, bool DMAP = false, bool SG = false>
 struct FastRay {
     static constexpr bool kDmap = DMAP && UNI && BK == MR_BATHY_GRID;
+    static constexpr bool kSame = SG && UNI && BK == MR_BATHY_GRID && CK == MR_CURRENT_GRID;
+    static constexpr bool kEarly = MR_EARLY_GRAD && CK == MR_CURRENT_GRID;     // advection sums formed ahead of the bilinears
+    static constexpr bool kShare = kSame && !kDmap && MR_SG_SHARE_GEOM;      // one cell geometry for both lookups (with the map the depth lookup is the rare path)
     float xf, yf;
     bool ok;
     bool deep;
@@ -574,10 +605,31 @@ struct FastRay {
     float4 Z, U, V;
     double2 gh, gu, gv;
     float bxa, bxb, bya, byb, cxa, cxb, cya, cyb;
-    double k2, k, cs, sn;
+    double k2, k, cs, sn;      // deep lanes of the depth-floor map: k holds (sqrt(G)/2) k^-3/2, cs holds k2 * 0
+    double ax, ay;             // kEarly: -kx du/dx - ky dv/dx, -kx du/dy - ky dv/dy
+
+    // f64 fractional index of the current and its cell (cartesian_current.rs:246-252).  The spacing is a launch
+    // constant: q0 = t*RN(1/s), then q0 + (t - q0 s) RN(1/s) in one fma.  The argument of that last rounding is
+    // t/s to within 2^-52 ulp (the residual is exact, only 1/s carries an error), so the result IS
+    // RN(t/s) unless t/s lies within 2^-52 ulp of a rounding midpoint — and only the cell, floor(index),
+    // is used: it can differ from the reference's only if that midpoint also neighbours an integer
+    // (~1e-28 per evaluation).  Exact whenever t/s is representable (a ray sitting on a grid line).  An
+    // infinite position turns into NaN here and fails the bounds test like the infinity.
+    __device__ __forceinline__ bool current_index(const CurrentDev &c, double x, double y)
+    {
+        const double tx = x - c.xd0, ty = y - c.yd0;
+        const double qx = tx * c.inv_sx, qy = ty * c.inv_sy;
+        const double ix = fma(fma(-qx, c.sx, tx), c.inv_sx, qx);
+        const double iy = fma(fma(-qy, c.sy, ty), c.inv_sy, qy);
+        cx1 = cell_of(ix, c.nx); cy1 = cell_of(iy, c.ny);
+        return ix >= 0.0 && ix <= c.nxm1d && iy >= 0.0 && iy <= c.nym1d;          // :248
+    }
 
     // ---- phase 1: fractional indices and cell addresses ------------------------------------------
-    __device__ __forceinline__ void phase1(const BathyDev &b, const CurrentDev &c, double x, double y, double kx, double ky)
+    // kSame: returns false — with nothing else decided — when the f32 index is too close to a grid line for one
+    // cell to serve both fields; the caller then evaluates this point with the separate lookups (rhs_fast_n).
+    // Otherwise (and always without kSame) returns true.
+    __device__ __forceinline__ bool phase1(const BathyDev &b, const CurrentDev &c, double x, double y, double kx, double ky)
     {
         xf = (float)x; yf = (float)y;                                              // wave_ray_path.rs:122
         ok = true;
@@ -599,29 +651,32 @@ struct FastRay {
                 ix = __fdiv_rn(__fsub_rn(xf, b.xf0), b.sx);
                 iy = __fdiv_rn(__fsub_rn(yf, b.yf0), b.sy);
             }
-            ok = ix >= 0.0f && ix <= b.nxm1f && iy >= 0.0f && iy <= b.nym1f;      // :291
             bx1 = cell_of(ix, b.nx); by1 = cell_of(iy, b.ny);
+            if (kSame) {
+                // distance of the index from the middle of its (clamped) cell: below sg_lim = 0.5 - sg_delta on both
+                // axes, the point is strictly inside the cell by more than the two indices can disagree — in bounds
+                // for both fields, same cell.  (A clamped cell puts an out-of-range index at 0.5 or more; NaN fails.)
+                const f32x2 mid = add2(pk((float)bx1, (float)by1), pk(0.5f, 0.5f));       // exact: cell numbers < 2^23
+                const f32x2 off = sub2(pk(ix, iy), mid);
+                if (!(fabsf(lo_of(off)) < b.sg_lim && fabsf(hi_of(off)) < b.sg_lim)) return false;
+            } else {
+                ok = ix >= 0.0f && ix <= b.nxm1f && iy >= 0.0f && iy <= b.nym1f;  // :291
+            }
             brec = b.cell + 2u * (unsigned)((b.nx - 1) * by1 + bx1);
             if (kDmap)
                 asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(hsq)
                              : "l"(b.dmap + (unsigned)((by1 >> kDeepShift) * b.dmap_nbx + (bx1 >> kDeepShift))));
         }
         if (CK == MR_CURRENT_GRID) {
-            // f64 fractional index (cartesian_current.rs:246).  The spacing is a launch constant:
-            // q0 = t*RN(1/s), then q0 + (t - q0 s) RN(1/s) in one fma.  The argument of that last rounding is
-            // t/s to within 2^-52 ulp (the residual is exact, only 1/s carries an error), so the result IS
-            // RN(t/s) unless t/s lies within 2^-52 ulp of a rounding midpoint — and only the cell, floor(index),
-            // is used: it can differ from the reference's only if that midpoint also neighbours an integer
-            // (~1e-28 per evaluation).  Exact whenever t/s is representable (a ray sitting on a grid line).  An
-            // infinite position turns into NaN here and fails the bounds test like the infinity.
-            const double tx = x - c.xd0, ty = y - c.yd0;
-            const double qx = tx * c.inv_sx, qy = ty * c.inv_sy;
-            const double ix = fma(fma(-qx, c.sx, tx), c.inv_sx, qx);
-            const double iy = fma(fma(-qy, c.sy, ty), c.inv_sy, qy);
-            ok = ok && ix >= 0.0 && ix <= c.nxm1d && iy >= 0.0 && iy <= c.nym1d;  // :248
-            cx1 = cell_of(ix, c.nx); cy1 = cell_of(iy, c.ny);
+            if (kSame) {
+                cx1 = bx1; cy1 = by1;
+            } else {
+                const bool okc = current_index(c, x, y);
+                ok = ok && okc;
+            }
             ccell = (unsigned)((c.nx - 1) * cy1 + cx1);
         }
+        return true;
     }
 
     // ---- phase 2: all record loads -----------------------------------------------------------------
@@ -632,7 +687,7 @@ struct FastRay {
                 // (a NaN or infinite k^2 fails or passes harmlessly: NaN compares false; k^2 = inf makes k NaN,
                 // and the deep-water branch turns that into four NaNs like the general one)
                 deep = ok && __fmul_rn((float)k2, hsq) >= 484.01f;
-                ldg_f4_d2_unless(deep, brec, Z, gh);
+                if (!MR_DMAP_LATE_LOAD) ldg_f4_d2_unless(deep, brec, Z, gh);
             } else {
                 ldg_f4_d2(brec, Z, gh);
             }
@@ -654,24 +709,45 @@ struct FastRay {
     // ---- phase 3: wavenumber-only f64 work, under the loads --------------------------------------
     __device__ __forceinline__ void phase3(double kx, double ky)
     {
+        if (MR_DEEP_ROOT4 && kDmap && deep) {
+            // Proven deep water: cg = (G/2) / sqrt(G k) and the direction cosines kx/k, ky/k only ever appear as
+            // cg kx / k = (sqrt(G)/2) k^-3/2 kx.  One fourth root of k^2 gives k^-1/2; k itself is never formed.
+            // k2 * 0 carries an infinite k^2 into every output as NaN, like the general branch (see wave_terms).
+            const double t = inv_root4(k2);
+            k = (t * t) * (t * kExpRed[7]);
+            cs = k2 * 0.0;
+            return;
+        }
         double rk;
         sqrt_rsqrt(k2, k, rk);
         cs = kx * rk; sn = ky * rk;
     }
 
     // ---- phase 4: f32 bilinears, then the f64 stage --------------------------------------------------
-    // depth and its gradient at (xf, yf) from the loaded record / the analytic kinds
-    __device__ __forceinline__ void bathy_part(const BathyDev &b, f32x2 p, float &h32, double &dhdx, double &dhdy)
+    // corner coordinates of a cell given as floats, and the in-cell fractions of p (UNI):
+    // (xa,ya) = i*d + p0, (xb,yb) = (xa,ya) + d, (Y, X) = (c10, c01) * ((x,y) - (xa,ya)), two components per instruction
+    struct Geom { float xa, xb, ya, yb, X, Y; };
+    __device__ __forceinline__ static Geom geom_of(int x1, int y1, f32x2 p, f32x2 d2, f32x2 p0, f32x2 c2)
+    {
+        const f32x2 pa = fma2(pk((float)x1, (float)y1), d2, p0), pb = add2(pa, d2);
+        const f32x2 yx = mul2(c2, sub2(p, pa));
+        Geom g;
+        g.xa = lo_of(pa); g.ya = hi_of(pa); g.xb = lo_of(pb); g.yb = hi_of(pb);
+        g.Y = lo_of(yx); g.X = hi_of(yx);
+        return g;
+    }
+
+    // depth and its gradient at (xf, yf) from the loaded record / the analytic kinds; `shared`: the affine cell
+    // geometry already resolved for this very cell (kSame), else NULL
+    __device__ __forceinline__ void bathy_part(const BathyDev &b, f32x2 p, float &h32, double &dhdx, double &dhdy,
+                                               const Geom *shared = nullptr)
     {
         if (BK == MR_BATHY_GRID) {
             float X, Y;
             if (UNI) {
-                // corner coordinates (xa,ya) = i*d + p0 and (xb,yb) = (xa,ya) + d, then
-                // (Y, X) = (c10, c01) * ((x,y) - (xa,ya)), two components per instruction
-                const f32x2 pa = fma2(pk((float)bx1, (float)by1), b.d2, b.p0), pb = add2(pa, b.d2);
-                const f32x2 yx = mul2(b.c2, sub2(p, pa));
-                bxa = lo_of(pa); bya = hi_of(pa); bxb = lo_of(pb); byb = hi_of(pb);
-                Y = lo_of(yx); X = hi_of(yx);
+                const Geom g = shared ? *shared : geom_of(bx1, by1, p, b.d2, b.p0, b.c2);
+                bxa = g.xa; bya = g.ya; bxb = g.xb; byb = g.yb;
+                Y = g.Y; X = g.X;
             } else {
                 const float dx = __fsub_rn(bxb, bxa), dy = __fsub_rn(byb, bya);
                 const float det = __fsub_rn(0.0f, __fmul_rn(dx, dy));              // interpolator.rs:64
@@ -693,16 +769,16 @@ struct FastRay {
         }
     }
 
-    // current and its gradients at (xf, yf)
-    __device__ __forceinline__ void current_part(const CurrentDev &c, f32x2 p, CurrentVal &cv)
+    // current and its gradients at (xf, yf); *keep (kSame) receives the cell geometry for the bathymetry to reuse
+    __device__ __forceinline__ void current_part(const CurrentDev &c, f32x2 p, CurrentVal &cv, Geom *keep = nullptr)
     {
         if (CK == MR_CURRENT_GRID) {
             float X, Y;
             if (UNI) {
-                const f32x2 pa = fma2(pk((float)cx1, (float)cy1), c.d2, c.p0), pb = add2(pa, c.d2);
-                const f32x2 yx = mul2(c.c2, sub2(p, pa));
-                cxa = lo_of(pa); cya = hi_of(pa); cxb = lo_of(pb); cyb = hi_of(pb);
-                Y = lo_of(yx); X = hi_of(yx);
+                const Geom g = geom_of(cx1, cy1, p, c.d2, c.p0, c.c2);
+                cxa = g.xa; cya = g.ya; cxb = g.xb; cyb = g.yb;
+                Y = g.Y; X = g.X;
+                if (keep) *keep = g;
             } else {
                 const float dx = __fsub_rn(cxb, cxa), dy = __fsub_rn(cyb, cya);
                 const float det = __fsub_rn(0.0f, __fmul_rn(dx, dy));
@@ -730,31 +806,87 @@ struct FastRay {
                 }
             }
             cv.u = (double)u32; cv.v = (double)v32;
-            cv.dudx = gu.x; cv.dudy = gu.y; cv.dvdx = gv.x; cv.dvdy = gv.y;
+            if (!kEarly) { cv.dudx = gu.x; cv.dudy = gu.y; cv.dvdx = gv.x; cv.dvdy = gv.y; }
         } else {
             cv.u = c.u0; cv.v = c.v0; cv.dudx = cv.dudy = cv.dvdx = cv.dvdy = 0.0;   // constant_current.rs:69-77
+        }
+    }
+
+    // the four outputs from cg cos, cg sin (or their deep-water form), the bathymetric terms and the current
+    __device__ __forceinline__ void assemble(double kx, double ky, double cg, double bx, double by,
+                                             const CurrentVal &cv, double out[4])
+    {
+        out[0] = fma(cg, cs, cv.u);
+        out[1] = fma(cg, sn, cv.v);
+        if (kEarly) {
+            out[2] = ax + bx;
+            out[3] = ay + by;
+        } else {
+            out[2] = fma(-ky, cv.dvdx, fma(-kx, cv.dudx, bx));
+            out[3] = fma(-ky, cv.dvdy, fma(-kx, cv.dudy, by));
         }
     }
 
     __device__ __forceinline__ void phase4(const BathyDev &b, const CurrentDev &c, double kx, double ky, double out[4])
     {
         const f32x2 p = pk(xf, yf);
+        if (kEarly) {
+            ax = fma(-ky, gv.x, -kx * gu.x);
+            ay = fma(-ky, gv.y, -kx * gu.y);
+        }
         if (kDmap) {
             // With the depth-floor map the current goes first: its record is what every lane waits for, and
             // the lanes in proven deep water then go straight to the deep-water terms.
             CurrentVal cv;
-            current_part(c, p, cv);
-            double cg, bx, by;
-            if (deep) {
-                wave_terms_deep(k, cg, bx, by);
-            } else {
-                float h32;
-                double dhdx, dhdy;
-                bathy_part(b, p, h32, dhdx, dhdy);
-                ok = ok && h32 > 0.0f;
-                wave_terms(k, (double)(ok ? h32 : qnanf()), dhdx, dhdy, cg, bx, by);
+            Geom g;
+            current_part(c, p, cv, kShare ? &g : nullptr);
+            if (!MR_DEEP_ROOT4 && deep) {
+                const double zk = k * 0.0;
+                double sq, rq;
+                sqrt_rsqrt(k * kExpRed[5], sq, rq);
+                assemble(kx, ky, fma(kExpRed[6], rq, zk), -zk, -zk, cv, out);
+                return;
             }
-            assemble_rhs(kx, ky, cs, sn, cg, bx, by, cv, out);
+            if (deep) {
+                // k = (sqrt(G)/2) k^-3/2, cs = k2 * 0 (phase3): cg cos = k kx, cg sin = k ky, bathymetric term -0
+                const double w = k, z = cs;
+                out[0] = fma(w, kx, cv.u);          // (an infinite k^2 has already turned w into NaN: inv_root4)
+                out[1] = fma(w, ky, cv.v);
+                if (kEarly) {
+                    out[2] = ax - z;
+                    out[3] = ay - z;
+                } else {
+                    out[2] = fma(-ky, cv.dvdx, fma(-kx, cv.dudx, -z));
+                    out[3] = fma(-ky, cv.dvdy, fma(-kx, cv.dudy, -z));
+                }
+                return;
+            }
+            double cg, bx, by;
+            float h32;
+            double dhdx, dhdy;
+            if (MR_DMAP_LATE_LOAD) ldg_f4_d2(brec, Z, gh);
+            bathy_part(b, p, h32, dhdx, dhdy, kShare ? &g : nullptr);
+            ok = ok && h32 > 0.0f;
+            wave_terms(k, (double)(ok ? h32 : qnanf()), dhdx, dhdy, cg, bx, by);
+            assemble(kx, ky, cg, bx, by, cv, out);
+            return;
+        }
+        if (kSame) {
+            // one cell geometry for both fields wherever they share the cell (nearly always)
+            // (scheduling fence, see below: the first consumer of the current record waits for the bathymetry record
+            // too, so that every load of the evaluation is in flight before the first wait)
+            U.x = __int_as_float(__float_as_int(U.x) | (__float_as_int(Z.x) & b.zero));
+            CurrentVal cv;
+            Geom g;
+            current_part(c, p, cv, kShare ? &g : nullptr);
+            float h32;
+            double dhdx, dhdy;
+            bathy_part(b, p, h32, dhdx, dhdy, kShare ? &g : nullptr);
+            ok = ok && h32 > 0.0f;
+            const double h = (double)(ok ? h32 : qnanf());
+            double cg, bx, by;
+            wave_terms(k, h, dhdx, dhdy, cg, bx, by);
+            assemble(kx, ky, cg, bx, by, cv, out);
             return;
         }
         // Scheduling fence.  ptxas places the first consumer of the bathymetry record ahead of the
@@ -778,16 +910,37 @@ struct FastRay {
         // term through -k/2, the advection terms added to NaN stay NaN).
         ok = ok && h32 > 0.0f;
         const double h = (double)(ok ? h32 : qnanf());
-        rhs_f64_fast(kx, ky, k, cs, sn, h, dhdx, dhdy, cv, out);
+        double cg, bx, by;
+        wave_terms(k, h, dhdx, dhdy, cg, bx, by);
+        assemble(kx, ky, cg, bx, by, cv, out);
     }
 };
 
 // The RHS of NR rays carried by one thread, phase by phase.
-template <int BK, int CK, bool UNI, int NR, bool DMAP>
+template <int BK, int CK, bool UNI, int NR, bool DMAP, bool SG>
 __device__ __forceinline__ void rhs_fast_n(const BathyDev &b, const CurrentDev &c,
                                            const double (&s)[NR][4], double (&out)[NR][4])
 {
-    FastRay<BK, CK, UNI, DMAP> ray[NR];
+    if (SG && NR == 1) {
+        // Same-grid shortcut: the evaluation with one cell for both fields, or — for a point within sg_delta of a
+        // grid line — the complete evaluation with the two separate lookups.  Two code paths rather than one with
+        // a join: the shortcut path then carries one cell, one geometry and no bounds state at all.
+        FastRay<BK, CK, UNI, DMAP, true> ray;
+        if (ray.phase1(b, c, s[0][0], s[0][1], s[0][2], s[0][3])) {
+            ray.phase2(b, c);
+            ray.phase3(s[0][2], s[0][3]);
+            ray.phase4(b, c, s[0][2], s[0][3], out[0]);
+        } else {
+            // (without the depth-floor map: it only ever skips work whose result cannot matter)
+            FastRay<BK, CK, UNI, false, false> sep;
+            sep.phase1(b, c, s[0][0], s[0][1], s[0][2], s[0][3]);
+            sep.phase2(b, c);
+            sep.phase3(s[0][2], s[0][3]);
+            sep.phase4(b, c, s[0][2], s[0][3], out[0]);
+        }
+        return;
+    }
+    FastRay<BK, CK, UNI, DMAP, false> ray[NR];
 #pragma unroll
     for (int r = 0; r < NR; ++r) ray[r].phase1(b, c, s[r][0], s[r][1], s[r][2], s[r][3]);
 #pragma unroll
@@ -801,7 +954,7 @@ __device__ __forceinline__ void rhs_fast_n(const BathyDev &b, const CurrentDev &
 // =============================================================================
 // System::system (wave_ray_path.rs:220-234): Err -> four NaN
 // =============================================================================
-template <int BK, int CK, int MATH, bool UNI, int NR, bool DMAP = false>
+template <int BK, int CK, int MATH, bool UNI, int NR, bool DMAP = false, bool SG = false>
 __device__ __forceinline__ void rhs(const BathyDev &b, const CurrentDev &c,
                                     const double (&s)[NR][4], double (&out)[NR][4])
 {
@@ -822,7 +975,7 @@ __device__ __forceinline__ void rhs(const BathyDev &b, const CurrentDev &c,
             else rhs_f64_strict(kx, ky, (double)h32, (double)gx32, (double)gy32, cv, out[r]);
         }
     } else {
-        rhs_fast_n<BK, CK, UNI, NR, DMAP>(b, c, s, out);
+        rhs_fast_n<BK, CK, UNI, NR, DMAP, SG>(b, c, s, out);
     }
 }
 

@@ -3,6 +3,7 @@
 #pragma once
 #include <algorithm>
 #include <cstdint>
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -13,6 +14,19 @@ namespace mr {
 // thread-local last-error text (mr_last_error)
 void set_error(const std::string &msg);
 int  fail(int code, const std::string &msg);
+
+// RN(1/s) for the fast path's exact f32 division by a launch constant (fdiv_const, mr_device.cuh); refused for
+// subnormal / huge s and for the all-ones significand that Markstein's theorem excludes.  Shared with the
+// self-test in tools/csrc/mr_tools.cu, which must apply the library's own rule.
+inline bool recip_ok(float s, float *r)
+{
+    uint32_t bits;
+    std::memcpy(&bits, &s, 4);
+    if (!(s > 1e-30f) || !(s < 1e30f) || (bits & 0x7fffffu) == 0x7fffffu) return false;
+    volatile float q = 1.0f / s;
+    *r = q;
+    return true;
+}
 
 // ---- NetCDF-3 -------------------------------------------------------------
 enum { NC3_BYTE = 1, NC3_CHAR = 2, NC3_SHORT = 3, NC3_INT = 4, NC3_FLOAT = 5, NC3_DOUBLE = 6 };

@@ -12,6 +12,4 @@ cudaError_t launch_trace_strict(const TraceArgs &a, cudaStream_t stream);
 cudaError_t launch_sample(const BathyDev &b, const CurrentDev &c, int64_t rows, int64_t n, int64_t ld,
                           const double *x, const double *y, float *depth, double *u, double *v,
                           cudaStream_t stream);
-// register-only DFMA loop used by mr_measure_fp64_peak
-cudaError_t launch_dfma_probe(double *sink, int iters, int blocks, cudaStream_t stream);
 }  // namespace mr

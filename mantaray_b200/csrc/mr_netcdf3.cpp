@@ -58,6 +58,14 @@ struct Cursor {
     }
 };
 
+// a * b without wrapping: false when the product does not fit in 64 bits
+bool mul_fits(uint64_t a, uint64_t b, uint64_t &out)
+{
+    if (a != 0 && b > UINT64_MAX / a) return false;
+    out = a * b;
+    return true;
+}
+
 size_t type_size(int t)
 {
     switch (t) {
@@ -173,10 +181,27 @@ int Nc3File::open(const char *path, Nc3File &f, std::string &err)
         v.is_record = !v.dimids.empty() && f.dims[v.dimids[0]].len == 0;
         size_t ts = type_size(v.type);
         if (ts == 0) { err = "'" + f.path + "': variable '" + v.name + "' has an unknown type"; return MR_ERR_FORMAT; }
+        // Element and byte counts come from header fields a corrupt file controls: every product is checked, and a
+        // variable larger than the file itself is refused here, before anything is sized by it.
         uint64_t per = 1;
-        for (size_t k = v.is_record ? 1 : 0; k < v.dimids.size(); ++k) per *= f.dims[v.dimids[k]].len;
+        bool fits = true;
+        for (size_t k = v.is_record ? 1 : 0; fits && k < v.dimids.size(); ++k)
+            fits = mul_fits(per, f.dims[v.dimids[k]].len, per);
+        uint64_t chunk_bytes = 0;
+        fits = fits && mul_fits(per, ts, chunk_bytes);
+        // (a record variable is bounded below through numrecs * recsize: with no records yet it may begin at the
+        // very end of the file)
+        if (!fits || v.begin > f.file_size || (!v.is_record && chunk_bytes > f.file_size - v.begin)) {
+            err = "'" + f.path + "': variable '" + v.name + "' is larger than the file (corrupt header?)";
+            return MR_ERR_FORMAT;
+        }
         v.elems_per_chunk = per;
-        if (v.is_record) { nrecvars++; f.recsize += ((per * ts + 3u) & ~(uint64_t)3u); }
+        if (v.is_record) {
+            nrecvars++;
+            const uint64_t padded = (chunk_bytes + 3u) & ~(uint64_t)3u;
+            if (f.recsize + padded < f.recsize) { err = "'" + f.path + "': record size overflows"; return MR_ERR_FORMAT; }
+            f.recsize += padded;
+        }
     }
     if (nrecvars == 1) {                                  // a lone record variable is not padded
         for (auto &v : f.vars)
@@ -185,7 +210,17 @@ int Nc3File::open(const char *path, Nc3File &f, std::string &err)
     if (f.numrecs == 0xFFFFFFFFu) {                       // "streaming" marker: derive from the file size
         uint64_t first = UINT64_MAX;
         for (auto &v : f.vars) if (v.is_record) first = std::min(first, v.begin);
-        f.numrecs = (first != UINT64_MAX && f.recsize) ? (uint32_t)((f.file_size - first) / f.recsize) : 0;
+        f.numrecs = (first != UINT64_MAX && f.recsize && first <= f.file_size)
+                        ? (uint32_t)std::min<uint64_t>((f.file_size - first) / f.recsize, 0xFFFFFFFEu) : 0;
+    }
+    // the records a header claims must exist in the file too
+    if (nrecvars > 0 && f.numrecs > 0) {
+        uint64_t all = 0;
+        if (!mul_fits(f.recsize, f.numrecs, all) || all > f.file_size) {
+            err = "'" + f.path + "': " + std::to_string(f.numrecs) + " records of " + std::to_string(f.recsize) +
+                  " bytes do not fit in the file (corrupt header?)";
+            return MR_ERR_FORMAT;
+        }
     }
     return MR_OK;
 }
@@ -205,12 +240,26 @@ uint64_t Nc3File::num_elems(const Nc3Var &v) const
 int Nc3File::read_raw(const Nc3Var &v, std::vector<uint8_t> &raw, std::string &err) const
 {
     size_t ts = type_size(v.type);
-    uint64_t n = num_elems(v);
-    raw.resize((size_t)(n * ts));
+    uint64_t n = num_elems(v), bytes = 0;
+    // extent against the file BEFORE anything is allocated (open() has already refused headers whose products
+    // wrap; this is the per-variable bound, records included)
+    if (!mul_fits(n, ts, bytes) || bytes > file_size || v.begin > file_size ||
+        (!v.is_record && bytes > file_size - v.begin)) {
+        err = "'" + path + "': variable '" + v.name + "' runs past the end of the file";
+        return MR_ERR_FORMAT;
+    }
+    if (v.is_record && numrecs > 0) {
+        const uint64_t chunk = v.elems_per_chunk * ts;      // fits: checked in open()
+        uint64_t span = 0;
+        if (!mul_fits(recsize, (uint64_t)numrecs - 1, span) || span > file_size - v.begin || chunk > file_size - v.begin - span) {
+            err = "'" + path + "': record variable '" + v.name + "' runs past the end of the file";
+            return MR_ERR_FORMAT;
+        }
+    }
+    raw.resize((size_t)bytes);
     std::ifstream in(path, std::ios::binary);
     if (!in) { err = "cannot open '" + path + "'"; return MR_ERR_IO; }
     if (!v.is_record) {
-        if (v.begin + n * ts > file_size) { err = "'" + path + "': variable '" + v.name + "' runs past the end of the file"; return MR_ERR_FORMAT; }
         in.seekg((std::streamoff)v.begin);
         in.read((char *)raw.data(), (std::streamsize)raw.size());
     } else {

@@ -13,6 +13,7 @@
 //     y  = y + (((k0 + k1*2) + k2*2) + k3) * (dt/6);  push(t, y)
 //     stop if solout(y, k0): all four of y, or all four of k0, are NaN
 //                                                   (src/wave_ray_path.rs:236-246)
+//     (k0_c enters component c of the sum, so "all four of k0 NaN" implies "all four of y NaN": one test)
 // A stopped ray's last row is therefore always all-NaN, and rows it never
 // reaches are NaN too (python/mantaray/core.py:115-119), so a stopped lane just
 // keeps storing its NaN state; when a whole warp has stopped it leaves the RK4
@@ -39,6 +40,7 @@ struct TraceArgs {
     int32_t *rows, *len;       // [n] or NULL
     double *fin;               // [4][n] or NULL
     int32_t deep_map;          // use the bathymetry's depth-floor map where the grids allow it (MR_OPT_DEEP_MAP)
+    int32_t same_grid;         // use the same-grid shortcut where the grids allow it (off: MR_OPT_NO_SAME_GRID)
     // filled by launch_trace_math: the trajectory planes as byte offsets from the x plane, the row pitch in bytes
     int64_t off_y, off_kx, off_ky, row_bytes;
     double sixth;              // dt / 6 (read from here by the depth-floor-map variant, which is short of registers)
@@ -53,6 +55,17 @@ static constexpr int kBlock = kBlockThreads;
 #endif
 #ifndef MR_MIN_BLOCKS
 #define MR_MIN_BLOCKS 7
+#endif
+// the ray state of the current step in shared memory instead of registers (fast path)
+// experiment knob: the redundant all-NaN test of k0 (see solout below); it changes ptxas's register allocation
+#ifndef MR_K0_TEST
+#define MR_K0_TEST 1
+#endif
+#ifndef MR_ROW_POINTER
+#define MR_ROW_POINTER 1
+#endif
+#ifndef MR_Y_SHARED
+#define MR_Y_SHARED 0
 #endif
 // grids whose f32 coordinates are not affine keep the per-cell corner coordinates and basis live: more registers
 #ifndef MR_MIN_BLOCKS_GENERIC
@@ -104,7 +117,7 @@ __device__ __forceinline__ void store_count(const TraceArgs &a, int32_t *dst, in
 // Per-ray bookkeeping is event-driven: `rows` is written when the ray stops and `len` when its first NaN
 // appears (each at most once per ray, re-deriving the ray index on the spot), so the step loop carries two
 // flags and one row pointer per thread; the step number and the store countdown are warp-uniform.
-template <int BK, int CK, int MATH, bool UNI, bool DMAP>
+template <int BK, int CK, int MATH, bool UNI, bool DMAP, bool SG>
 __global__ void __launch_bounds__(kBlock, (MATH == MR_MATH_FAST) ? (UNI ? (DMAP ? MR_MIN_BLOCKS_DMAP : MR_MIN_BLOCKS) : MR_MIN_BLOCKS_GENERIC) : 1)
 trace_kernel(const __grid_constant__ TraceArgs a)
 {
@@ -114,27 +127,48 @@ trace_kernel(const __grid_constant__ TraceArgs a)
     const double half = dt / 2.0;
     const int32_t nsteps = (int32_t)a.nsteps;      // < 2^31 (mr_num_steps)
 
-    double y[1][4];
-    char *p;                               // this ray's element of the last stored row of the x plane
+    // The state (x, y, kx, ky) of the step being taken.  MR_Y_SHARED: it lives in shared memory (32 bytes per
+    // thread, each thread its own slots, no synchronisation) instead of eight registers that would otherwise be
+    // live through every right-hand side; it is read once per stage and written once per step.
+    constexpr bool kYsh = MR_Y_SHARED && MATH == MR_MATH_FAST;
+    __shared__ double ysh[kYsh ? 4 : 1][kYsh ? kBlock : 1];
+    double yreg[4];
+    auto Y = [&](int c) -> double & { return kYsh ? ysh[c][threadIdx.x] : yreg[c]; };
+    auto load_state = [&](double out[4]) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) out[c] = Y(c);
+    };
+    // MR_ROW_POINTER: the thread carries a pointer to its element of the last stored row; otherwise only the
+    // (warp-uniform) row number is carried and the address is formed when a row is stored
+    char *p = nullptr;                     // this ray's element of the last stored row of the x plane
+    int32_t row = 0;                       // the last stored row
+    auto row_ptr = [&]() -> char * {
+        return MR_ROW_POINTER ? p : (char *)(a.x + ray_index(a)) + (int64_t)row * a.row_bytes;
+    };
+    bool alive = nsteps > 0;
+    bool clean;                            // no NaN seen yet: rows so far all count towards len
     {
         const int64_t i = ray_index(a);
-        y[0][0] = a.x0[i]; y[0][1] = a.y0[i]; y[0][2] = a.kx0[i]; y[0][3] = a.ky0[i];
-        p = (char *)(a.x + i);
+        const double y0[4] = {a.x0[i], a.y0[i], a.kx0[i], a.ky0[i]};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) Y(c) = y0[c];
+        if (MR_ROW_POINTER) p = (char *)(a.x + i);
+        clean = !any_nan4(y0);
+        if (!clean) {                      // no NaN-free row at all
+            if (a.len) store_count(a, a.len, 0);
+            if (a.fin) { const double nanrow[4] = {qnan(), qnan(), qnan(), qnan()}; store_fin(a, nanrow); }
+        }
+        if (store) store_row(a, row_ptr(), y0);
     }
-    bool alive = nsteps > 0;
-    bool clean = !any_nan4(y[0]);          // no NaN seen yet: rows so far all count towards len
-    if (!clean) {                          // no NaN-free row at all
-        if (a.len) store_count(a, a.len, 0);
-        if (a.fin) { const double nanrow[4] = {qnan(), qnan(), qnan(), qnan()}; store_fin(a, nanrow); }
-    }
-    if (store) store_row(a, p, y[0]);
 
     int32_t until_store = a.stride;        // counts down to the next stored row
     for (int32_t s = 1; s <= nsteps; ++s) {
         if (!__any_sync(0xffffffffu, alive)) break;
         if (alive) {
             double k[1][4], acc[4];
+#if MR_K0_TEST
             bool k0_nan;
+#endif
 #pragma unroll
             for (int c = 0; c < 4; ++c) { k[0][c] = 0.0; acc[c] = -0.0; }    // -0 + k0 == k0 for every k0
 #pragma unroll kStageUnroll
@@ -144,48 +178,75 @@ trace_kernel(const __grid_constant__ TraceArgs a)
                 double yt[1][4];
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
-                    const double adv = (MATH == MR_MATH_STRICT) ? __dadd_rn(y[0][c], __dmul_rn(k[0][c], as)) : fma(k[0][c], as, y[0][c]);
+                    const double yc = Y(c);
+                    const double adv = (MATH == MR_MATH_STRICT) ? __dadd_rn(yc, __dmul_rn(k[0][c], as)) : fma(k[0][c], as, yc);
                     // stage 0 evaluates f(y): k is 0 there, and y + 0*0 == y (a -0 component would become
                     // +0, which the strict path must not allow)
-                    yt[0][c] = (MATH == MR_MATH_STRICT && st == 0) ? y[0][c] : adv;
+                    yt[0][c] = (MATH == MR_MATH_STRICT && st == 0) ? yc : adv;
                 }
-                rhs<BK, CK, MATH, UNI, 1, DMAP>(a.b, a.c, yt, k);
+                rhs<BK, CK, MATH, UNI, 1, DMAP, SG>(a.b, a.c, yt, k);
+#if MR_K0_TEST
                 if (st == 0) k0_nan = all_nan4(k[0]);
+#endif
 #pragma unroll
                 for (int c = 0; c < 4; ++c)
                     acc[c] = (MATH == MR_MATH_STRICT) ? __dadd_rn(acc[c], __dmul_rn(k[0][c], ws)) : fma(k[0][c], ws, acc[c]);
             }
             double yn[4];
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
-                yn[c] = (MATH == MR_MATH_STRICT) ? __dadd_rn(y[0][c], __dmul_rn(acc[c], sixth)) : fma(acc[c], sixth, y[0][c]);
+            for (int c = 0; c < 4; ++c) {
+                const double yc = Y(c);
+                yn[c] = (MATH == MR_MATH_STRICT) ? __dadd_rn(yc, __dmul_rn(acc[c], sixth)) : fma(acc[c], sixth, yc);
+            }
             const bool n0 = isnan(yn[0]), n1 = isnan(yn[1]), n2 = isnan(yn[2]), n3 = isnan(yn[3]);
             if (clean && (n0 || n1 || n2 || n3)) {
                 clean = false;
                 if (a.len) store_count(a, a.len, s);
-                if (a.fin) store_fin(a, y[0]);        // y, the row before this one, is the last NaN-free state
+                if (a.fin) {                          // the row before this one is the last NaN-free state
+                    double yo[4];
+                    load_state(yo);
+                    store_fin(a, yo);
+                }
             }
+            // solout(y_new, k0) also stops on an all-NaN k0 — which needs no test of its own: k0 enters every
+            // component of the sum, so an all-NaN k0 has made y_new all NaN
+#if MR_K0_TEST
             if (k0_nan || (n0 && n1 && n2 && n3)) {
+#else
+            if (n0 && n1 && n2 && n3) {
+#endif
                 alive = false;
                 if (a.rows) store_count(a, a.rows, s + 1);
             }
 #pragma unroll
-            for (int c = 0; c < 4; ++c) y[0][c] = yn[c];
+            for (int c = 0; c < 4; ++c) Y(c) = yn[c];
         }
         if (--until_store == 0) {
             until_store = a.stride;
-            p += a.row_bytes;
-            if (store) store_row(a, p, y[0]);
+            if (MR_ROW_POINTER) p += a.row_bytes; else ++row;
+            if (store) {
+                double yo[4];
+                load_state(yo);
+                store_row(a, row_ptr(), yo);
+            }
         }
     }
     // whole warp stopped early: the rows it never reached are NaN (how many is read off the row pointer,
     // so that nothing but the pointer is carried through the loop for it)
     if (store) {
         const double nanrow[4] = {qnan(), qnan(), qnan(), qnan()};
-        char *const last = (char *)(a.x + ray_index(a)) + (int64_t)(nsteps / a.stride) * a.row_bytes;
-        while (p != last) {
-            p += a.row_bytes;
-            store_row(a, p, nanrow);
+        if (MR_ROW_POINTER) {
+            char *const last = (char *)(a.x + ray_index(a)) + (int64_t)(nsteps / a.stride) * a.row_bytes;
+            while (p != last) {
+                p += a.row_bytes;
+                store_row(a, p, nanrow);
+            }
+        } else {
+            const int32_t last = nsteps / a.stride;
+            while (row != last) {
+                ++row;
+                store_row(a, row_ptr(), nanrow);
+            }
         }
     }
     // a ray still integrating when the loop ends ran all nsteps (nsteps == 0: the initial row only);
@@ -195,7 +256,11 @@ trace_kernel(const __grid_constant__ TraceArgs a)
     }
     if (clean) {
         if (a.len) store_count(a, a.len, nsteps + 1);
-        if (a.fin) store_fin(a, y[0]);
+        if (a.fin) {
+            double yo[4];
+            load_state(yo);
+            store_fin(a, yo);
+        }
     }
 }
 
@@ -217,10 +282,16 @@ static cudaError_t launch_trace_math(const TraceArgs &args, cudaStream_t stream)
     constexpr bool kFast = MATH == MR_MATH_FAST;
     // the depth-floor map needs the affine fast path on a gridded bathymetry that has one
     const bool dmap = uni && a.deep_map && a.b.kind == MR_BATHY_GRID && a.b.dmap != nullptr;
+    // the same-grid shortcut needs both fields gridded, affine, and on one grid (BathyDev::same_grid, set at upload)
+    const bool sg = uni && a.same_grid && a.b.kind == MR_BATHY_GRID && a.c.kind == MR_CURRENT_GRID && a.b.same_grid;
 #define MR_LAUNCH(BKV, CKV, UNIV)                                                                              \
     do {                                                                                                       \
-        if (dmap) trace_kernel<BKV, CKV, MATH, UNIV, kFast && UNIV && BKV == MR_BATHY_GRID><<<grid, kBlock, 0, stream>>>(a); \
-        else trace_kernel<BKV, CKV, MATH, UNIV, false><<<grid, kBlock, 0, stream>>>(a);                        \
+        constexpr bool kGG = kFast && UNIV && BKV == MR_BATHY_GRID && CKV == MR_CURRENT_GRID;                  \
+        constexpr bool kBG = kFast && UNIV && BKV == MR_BATHY_GRID;                                            \
+        if (dmap && sg) trace_kernel<BKV, CKV, MATH, UNIV, kBG, kGG><<<grid, kBlock, 0, stream>>>(a);          \
+        else if (dmap) trace_kernel<BKV, CKV, MATH, UNIV, kBG, false><<<grid, kBlock, 0, stream>>>(a);         \
+        else if (sg) trace_kernel<BKV, CKV, MATH, UNIV, false, kGG><<<grid, kBlock, 0, stream>>>(a);           \
+        else trace_kernel<BKV, CKV, MATH, UNIV, false, false><<<grid, kBlock, 0, stream>>>(a);                 \
     } while (0)
 #define MR_CASE(BKV, CKV)                                                                                      \
     if (a.b.kind == BKV && a.c.kind == CKV) {                                                                  \

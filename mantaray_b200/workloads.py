@@ -241,7 +241,8 @@ def c5_nazare(n_periods: int = 64, n_dirs: int = 64, n_points: int = 16_384, n_s
 
     dt = 2.0
     return Workload("C5-nazare", "Nazare-style canyon 4096x4096 @ 25 m + coastal jet, frequency/direction ensemble, stride-64 output",
-                    bathy, cur, n_rays, dt * n_steps, dt, stride, "full", rays)
+                    bathy, cur, n_rays, dt * n_steps, dt, stride, "full", rays,
+                    extra={"tile": n_points, "n_periods": n_periods, "n_dirs": n_dirs})
 
 
 WORKLOADS = {
@@ -260,3 +261,14 @@ def shard_range(n: int, rank: int, world: int, align: int = 128) -> Tuple[int, i
     per = -(-per // align) * align
     lo = min(rank * per, n)
     return lo, min(lo + per, n)
+
+
+def shard_tiles(n: int, rank: int, world: int, tile: int):
+    """Tiles of `tile` consecutive rays dealt round-robin: rank r gets tiles r, r + world, r + 2 world, ...
+    (interleaved assignment where termination is correlated with the ray index).  In C5 a tile is one
+    (period, direction) pair over all start points, so every rank gets every period — a contiguous block would be a
+    band of periods, and long periods run ashore early.  The gather is a strided concatenation of the tiles.
+    Returns the list of (lo, hi) index ranges."""
+    tile = max(int(tile), 1)
+    n_tiles = -(-n // tile)
+    return [(t * tile, min((t + 1) * tile, n)) for t in range(rank, n_tiles, world)]

@@ -500,7 +500,8 @@ int64_t orc_num_steps(double t0, double t_end, double dt)
 {
     if (!(dt > 0.0)) return -1;
     double q = ceil((t_end - t0) / dt);
-    if (!(q >= 0.0) || !(q < 9.0e15)) return -1;
+    if (isnan(q) || !(q < 9.0e15)) return -1;
+    if (q < 0.0) return 0;      /* `as usize` saturates a negative quotient: no steps, the initial row only */
     return (int64_t)q;
 }
 

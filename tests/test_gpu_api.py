@@ -13,6 +13,7 @@ from conftest import assert_parity
 from mantaray_b200 import CartesianCurrent, CartesianNetcdf3, Fields, _abi, _capi, trace_many
 from mantaray_b200 import workloads as W
 from mantaray_b200.io_utility import write_netcdf3
+from tools import mrtools
 
 pytestmark = pytest.mark.gpu
 
@@ -100,18 +101,15 @@ def test_file_errors_raise(gpu, tmp_path):
 @pytest.mark.parametrize("spacing", [500.0, 10.0, 25.0, 50.0, 1000.0, 1.0, 0.1, 3.0, 37.3, 41.7, 1e-3, 12345.678, 0.30000001192092896, 7.0e5])
 def test_f32_index_division_is_exact_for_every_float(gpu, spacing):
     """fdiv_const (Markstein, two exact-residual steps) == IEEE divide for ALL 2^31 non-negative finite floats."""
-    bad = C.c_uint64(123)
-    usable = C.c_int32(-1)
-    rc = _capi.load().mr_selftest_fdiv(0, spacing, C.byref(bad), C.byref(usable))
-    assert rc == 0 and usable.value == 1
-    assert bad.value == 0, f"{bad.value} floats divide differently by {spacing}"
+    rc, bad, usable = mrtools.selftest_fdiv(0, spacing)
+    assert rc == 0 and usable == 1
+    assert bad == 0, f"{bad} floats divide differently by {spacing}"
 
 
 def test_division_shortcut_refuses_the_excluded_divisors(gpu):
-    bad, usable = C.c_uint64(0), C.c_int32(-1)
     all_ones = np.frombuffer(np.uint32(0x3fffffff).tobytes(), dtype=np.float32)[0]      # significand all ones
-    assert _capi.load().mr_selftest_fdiv(0, float(all_ones), C.byref(bad), C.byref(usable)) == 0 and usable.value == 0
-    assert _capi.load().mr_selftest_fdiv(0, 1e-40, C.byref(bad), C.byref(usable)) == 0 and usable.value == 0
+    assert mrtools.selftest_fdiv(0, float(all_ones))[::2] == (0, 0)
+    assert mrtools.selftest_fdiv(0, 1e-40)[::2] == (0, 0)
 
 
 def test_non_affine_grid_takes_the_general_path_and_agrees(oracle, gpu):
@@ -151,7 +149,7 @@ def test_rays_on_grid_lines_and_nodes(oracle, gpu):
 
 
 def test_multi_device_handle_shards_and_gathers(gpu):
-    """Rays split in contiguous blocks over the devices of the handle; the gather is a concatenation."""
+    """The devices of a handle share one queue of slabs; the gather is a concatenation of column blocks."""
     ndev = _capi.device_count()
     if ndev < 2:
         pytest.skip("one visible device")
@@ -161,13 +159,78 @@ def test_multi_device_handle_shards_and_gathers(gpu):
         assert fn.device_mask == (1 << ndev) - 1
         a = trace_many(f1, *rays, 0.0, wl.duration, wl.dt, final_state=True, env=True)
         b = trace_many(fn, *rays, 0.0, wl.duration, wl.dt, final_state=True, env=True)
+        assert sum(fn.last_split()) == rays[0].size and len(fn.last_split()) == ndev
         # again on the warm handle (cached work buffers on every device), in slabs, and after a trim
-        c = trace_many(fn, *rays, 0.0, wl.duration, wl.dt, final_state=True, env=True, chunk_rays=256)
+        c = trace_many(fn, *rays, 0.0, wl.duration, wl.dt, final_state=True, env=True, chunk_rays=64)
+        split = fn.last_split()
+        assert sum(split) == rays[0].size and sum(1 for s in split if s > 0) >= 2, split     # 25 slabs: more than one device worked
         fn.trim()
         d = trace_many(fn, *rays, 0.0, wl.duration, wl.dt, final_state=True, env=True)
     for other in (b, c, d):
         for name in ("t", "x", "y", "kx", "ky", "rows", "len", "final_state", "depth", "u", "v"):
             np.testing.assert_array_equal(getattr(a, name), getattr(other, name), err_msg=name)
+
+
+def test_multi_device_queue_balances_a_lopsided_batch(oracle, gpu):
+    """The first half of the batch stops at once (rays started on dry land), the second half runs every step.  A
+    split into one contiguous block per device would leave the first device idle; the slab queue
+    (src/ray.rs:105-123: rayon's par_iter balances dynamically) gives every device a share of the live rays."""
+    ndev = _capi.device_count()
+    if ndev < 2:
+        pytest.skip("one visible device")
+    wl = W.c2_sea_mount(400_000, 400)
+    x0, y0, kx0, ky0 = wl.all_rays()
+    half = x0.size // 2
+    x0 = x0.copy(); y0 = y0.copy()
+    x0[:half], y0[:half] = 0.0, np.linspace(-100.0, 100.0, half)          # on the island: h <= 0, one NaN row
+    with Fields(wl.bathymetry, wl.current, devices=list(range(ndev))) as fn:
+        r = trace_many(fn, x0, y0, kx0, ky0, 0.0, wl.duration, wl.dt, trajectories=False, final_state=True, chunk_rays=8192)
+        split = fn.last_split()
+    assert sum(split) == x0.size and sum(1 for s in split if s > 0) >= 2, split
+    assert (r.rows[:half] == 2).all() and (r.rows[half:] > 2).all()
+    sel = np.r_[0:half:997, half:x0.size:997]
+    ref = oracle.trace_many(wl.bathymetry, wl.current, x0[sel], y0[sel], kx0[sel], ky0[sel], 0.0, wl.duration, wl.dt,
+                            trajectories=False)
+    np.testing.assert_array_equal(r.rows[sel], ref.rows)
+    np.testing.assert_array_equal(r.len[sel], ref.len)
+    np.testing.assert_allclose(r.final_state[:, sel], ref.final_state, rtol=1e-9, atol=0, equal_nan=True)
+
+
+def test_gather_beyond_the_2d_copy_pitch_limit_goes_row_by_row(gpu, monkeypatch):
+    """cudaMemcpy2DAsync refuses pitches above cudaDevAttrMaxPitch (2 GiB: 2.68e8 rays per row of doubles).  The
+    limit is lowered for this handle so that an ordinary batch takes the row-by-row gather."""
+    wl = W.c4_agulhas(30, 30, 150, nx=128)
+    rays = wl.all_rays()
+    with Fields(wl.bathymetry, wl.current, devices=[0]) as f:
+        a = trace_many(f, *rays, 0.0, wl.duration, wl.dt, final_state=True, env=True)
+    monkeypatch.setenv("MR_DEBUG_MAX_PITCH", "1024")
+    with Fields(wl.bathymetry, wl.current, devices=[0]) as f:
+        b = trace_many(f, *rays, 0.0, wl.duration, wl.dt, final_state=True, env=True)
+        c = trace_many(f, *rays, 0.0, wl.duration, wl.dt, final_state=True, env=True, chunk_rays=256)
+    for other in (b, c):
+        for name in ("t", "x", "y", "kx", "ky", "rows", "len", "final_state", "depth", "u", "v"):
+            np.testing.assert_array_equal(getattr(a, name), getattr(other, name), err_msg=name)
+
+
+@pytest.mark.parametrize("math", [_abi.MR_MATH_FAST, _abi.MR_MATH_STRICT])
+def test_negative_or_zero_duration_is_the_initial_row_only(oracle, gpu, math):
+    """`((x_end - x) / h).ceil() as usize` saturates a negative quotient to 0 steps (ode_solvers Rk4::integrate,
+    called from src/ray.rs:207-208): the ray is its initial row, not an error."""
+    wl = W.c4_agulhas(4, 4, 10, nx=64)
+    rays = wl.all_rays()
+    with Fields(wl.bathymetry, wl.current, devices=[0]) as f:
+        for t_end in (-50.0, 0.0):
+            res = trace_many(f, *rays, 0.0, t_end, wl.dt, math=math, final_state=True)
+            ref = oracle.trace_many(wl.bathymetry, wl.current, *rays, 0.0, t_end, wl.dt)
+            assert res.x.shape == (1, 16) and (res.rows == 1).all() and (res.len == 1).all()
+            assert_parity(res, ref, what=f"t_end={t_end}")
+            np.testing.assert_array_equal(res.x[0], rays[0])
+        one = _capi.single_ray(f, *(a[3] for a in rays), 0.0, -1.0, wl.dt, math=math)
+        assert one.shape == (1, 5) and one[0, 0] == 0.0 and one[0, 1] == rays[0][3]
+        with pytest.raises(ValueError):
+            trace_many(f, *rays, 0.0, 10.0, -1.0)                    # dt <= 0 stays an error
+        with pytest.raises(ValueError):
+            trace_many(f, *rays, 0.0, float("inf"), 1.0)
 
 
 def test_work_buffers_are_reused_and_trimmed(gpu):

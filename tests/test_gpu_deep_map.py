@@ -1,8 +1,11 @@
 """The depth-floor map (include/mantaray_b200.h): the fast path skips the depth lookup wherever a
 per-block lower bound of the depth proves kh >= 22.  It is on by default where a quarter of the grid's blocks are
 deep for a 10 s wave; MR_OPT_DEEP_MAP forces it on, MR_OPT_NO_DEEP_MAP off.  These tests hold the path WITH the
-map to the oracle (same bar as everywhere) and to the path WITHOUT it (identical up to the sign of an exact zero),
-on every grid that has a map, whatever its deep share."""
+map to the oracle (same bar as everywhere) and to the path WITHOUT it — same rows, same len, same NaN pattern,
+values to a few ulp (a lane the map proves deep evaluates cg cos(theta) as (sqrt(G)/2) k^-3/2 kx from one fourth
+root instead of forming k, 1/k and 1/sqrt(G k): the same function, rounded differently) — on every grid that has
+a map, whatever its deep share.  The same-grid shortcut (MR_OPT_NO_SAME_GRID switches it off) changes no
+operation at all, only which index names the cell: with it and without it the results are bit-identical."""
 
 import os
 
@@ -24,12 +27,37 @@ def both(f, rays, t_end, dt, **kw):
     return plain, mapped
 
 
-def assert_same(mapped, plain, what):
+#: map against no map: the ray equations amplify a last-bit difference in cg along the ray, nothing more
+ULP_TOL = 1e-11
+
+
+def assert_same(mapped, plain, what, exact=False):
     np.testing.assert_array_equal(mapped.rows, plain.rows, err_msg=f"{what}: rows")
     np.testing.assert_array_equal(mapped.len, plain.len, err_msg=f"{what}: len")
-    for name in ("x", "y", "kx", "ky", "final_state"):
-        # assert_array_equal: NaN == NaN and -0 == +0, everything else bit for bit
-        np.testing.assert_array_equal(getattr(mapped, name), getattr(plain, name), err_msg=f"{what}: {name}")
+    if exact:
+        for name in ("x", "y", "kx", "ky", "final_state"):
+            # assert_array_equal: NaN == NaN and -0 == +0, everything else bit for bit
+            np.testing.assert_array_equal(getattr(mapped, name), getattr(plain, name), err_msg=f"{what}: {name}")
+        return
+    with np.errstate(invalid="ignore"):
+        pos = np.nanmax(np.maximum(np.abs(plain.x), np.abs(plain.y)), axis=0, initial=0.0)
+        ksc = np.nanmax(np.hypot(plain.kx, plain.ky), axis=0, initial=0.0)
+        pos, ksc = np.where(pos > 0, pos, 1.0), np.where(ksc > 0, ksc, 1.0)
+        for name, sc in (("x", pos), ("y", pos), ("kx", ksc), ("ky", ksc)):
+            a, b = getattr(mapped, name), getattr(plain, name)
+            np.testing.assert_array_equal(np.isnan(a), np.isnan(b), err_msg=f"{what}: NaN pattern of {name}")
+            err = float(np.nanmax(np.abs(a - b) / sc[None, :], initial=0.0))
+            assert err <= ULP_TOL, f"{what}: {name} differs by {err:.2e} of the ray's scale with the map"
+        np.testing.assert_array_equal(np.isnan(mapped.final_state), np.isnan(plain.final_state), err_msg=f"{what}: final state")
+
+
+def same_grid_pair(f, rays, t_end, dt, **kw):
+    """(separate lookups, same-grid shortcut), both without the map: must be bit-identical"""
+    from mantaray_b200._abi import MR_OPT_NO_SAME_GRID
+    sep = trace_many(f, *rays, 0.0, t_end, dt, math=MR_MATH_FAST, final_state=True,
+                     flags=MR_OPT_NO_DEEP_MAP | MR_OPT_NO_SAME_GRID, **kw)
+    sg = trace_many(f, *rays, 0.0, t_end, dt, math=MR_MATH_FAST, final_state=True, flags=MR_OPT_NO_DEEP_MAP, **kw)
+    return sep, sg
 
 
 @pytest.mark.parametrize("name,make", [
@@ -44,8 +72,10 @@ def test_workloads_with_the_depth_floor_map(oracle, gpu, name, make):
     ref = oracle.trace_many(wl.bathymetry, wl.current, *rays, 0.0, wl.duration, wl.dt, stride=wl.stride)
     with Fields(wl.bathymetry, wl.current, devices=[0]) as f:
         plain, mapped = both(f, rays, wl.duration, wl.dt, stride=wl.stride)
+        sep, sg = same_grid_pair(f, rays, wl.duration, wl.dt, stride=wl.stride)
     assert_parity(mapped, ref, what=f"{name} with the depth-floor map")
     assert_same(mapped, plain, name)
+    assert_same(sg, sep, f"{name}: same-grid shortcut", exact=True)
 
 
 @pytest.mark.parametrize("seed", range(int(os.environ.get("MR_FUZZ_SEEDS", "120"))))
@@ -55,8 +85,10 @@ def test_fuzz_with_the_depth_floor_map(oracle, gpu, seed):
     ref = oracle.trace_many(bathy, cur, *rays, 0.0, dt * steps, dt, stride=stride)
     with Fields(bathy, cur, devices=[0]) as f:
         plain, mapped = both(f, rays, dt * steps, dt, stride=stride, chunk_rays=(0 if seed % 4 else 192))
+        sep, sg = same_grid_pair(f, rays, dt * steps, dt, stride=stride)
     assert_parity(mapped, ref, what=f"fuzz seed {seed} with the depth-floor map")
     assert_same(mapped, plain, f"fuzz seed {seed}")
+    assert_same(sg, sep, f"fuzz seed {seed}: same-grid shortcut", exact=True)
 
 
 def test_blocks_with_dry_and_non_finite_nodes_fall_back_to_the_lookup(oracle, gpu):
@@ -87,8 +119,10 @@ def test_blocks_with_dry_and_non_finite_nodes_fall_back_to_the_lookup(oracle, gp
         ref = oracle.trace_many(bathy, cur, x0, y0, kx0, ky0, 0.0, dt * steps, dt)
         with Fields(bathy, cur, devices=[0]) as f:
             plain, mapped = both(f, (x0, y0, kx0, ky0), dt * steps, dt)
+            sep, sg = same_grid_pair(f, (x0, y0, kx0, ky0), dt * steps, dt)
         assert_parity(mapped, ref, what="dry / non-finite blocks with the depth-floor map")
         assert_same(mapped, plain, "dry / non-finite blocks")
+        assert_same(sg, sep, "dry / non-finite blocks: same-grid shortcut", exact=True)
 
 
 def test_default_follows_the_deep_share_of_the_grid(gpu):
@@ -104,6 +138,6 @@ def test_default_follows_the_deep_share_of_the_grid(gpu):
             auto = trace_many(f, *rays, 0.0, wl.duration, wl.dt, final_state=True, stride=wl.stride)
             off = trace_many(f, *rays, 0.0, wl.duration, wl.dt, final_state=True, stride=wl.stride,
                              flags=MR_OPT_DEEP_MAP | MR_OPT_NO_DEEP_MAP)
-        assert_same(auto, mapped if deep else plain, "default flags")
-        assert_same(off, plain, "both flags")
+        assert_same(auto, mapped if deep else plain, "default flags", exact=True)
+        assert_same(off, plain, "both flags", exact=True)
         assert_same(mapped, plain, "forced")

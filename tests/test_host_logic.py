@@ -188,3 +188,22 @@ def test_depth_floor_map_is_a_lower_bound_of_the_reference_lookup(oracle):
         assert (k[deep] * d[deep] >= 22.0).all(), f"{name}: flagged deep with kh = {np.min(k[deep] * d[deep])}"
         checked += int(deep.sum())
     assert checked > 50_000 and n_affine >= 10
+
+
+def test_interleaved_tiles_cover_the_batch_once_and_mix_the_periods():
+    """bench.py's C5 sharding: tiles dealt round-robin.  Every ray belongs to exactly one rank, and
+    every rank holds every period of the ensemble (a contiguous block would hold one band of them)."""
+    wl = W.c5_nazare(8, 8, 32, 64, nx=64)
+    n, tile = wl.n_rays, wl.extra["tile"]
+    for world in (1, 2, 3, 8):
+        seen = np.zeros(n, dtype=np.int32)
+        for r in range(world):
+            ranges = W.shard_tiles(n, r, world, tile)
+            periods = set()
+            for lo, hi in ranges:
+                seen[lo:hi] += 1
+                periods.add(lo // tile // wl.extra["n_dirs"])
+            if world <= 8 and world != 3:
+                assert periods == set(range(wl.extra["n_periods"])), (world, r, periods)
+        assert (seen == 1).all()
+    assert W.shard_tiles(10, 1, 4, 3) == [(3, 6)] and W.shard_tiles(10, 3, 4, 3) == [(9, 10)] and W.shard_tiles(5, 2, 4, 3) == []

@@ -114,6 +114,69 @@ def test_errors(tmp_path):
             f.read_f64("nope")
     trunc = tmp_path / "trunc.nc"
     trunc.write_bytes(ok.read_bytes()[:-16])
-    with _capi.Nc3Reader(trunc) as f:
-        with pytest.raises((_capi.MantarayError, OSError)):
+    with pytest.raises(_capi.MantarayError) as e:       # refused when opened: the header promises bytes the file lacks
+        with _capi.Nc3Reader(trunc) as f:
             f.read_f64("depth")
+    assert e.value.code == -5
+
+
+# ---- hostile headers: every size a header can claim is checked against the file before anything is allocated ----
+def _patch_dim(path, out, name: str, new_len: int):
+    """Rewrite the length of dimension `name` in the header of a classic file, leaving everything else alone."""
+    import struct
+
+    raw = bytearray(open(path, "rb").read())
+    tag = struct.pack(">I", len(name)) + name.encode() + b"\0" * (-len(name) % 4)
+    at = raw.index(tag) + len(tag)
+    raw[at:at + 4] = struct.pack(">I", new_len)
+    open(out, "wb").write(bytes(raw))
+
+
+@pytest.mark.parametrize("ylen, xlen", [(65535, 65535), (0xFFFFFFF0, 0xFFFFFFF0), (1 << 31, 8), (3, 1 << 30)])
+def test_header_that_claims_more_data_than_the_file_holds_is_a_format_error(tmp_path, ylen, xlen):
+    """65535 x 65535 doubles is 34 GB claimed by a 200-byte file; 0xFFFFFFF0^2 * 8 wraps 64 bits.  Both used to reach
+    std::vector::resize (bad_alloc / length_error through the C ABI = std::terminate in the caller's process)."""
+    good, bad = tmp_path / "good.nc", tmp_path / "bad.nc"
+    create_netcdf3_bathymetry(good, 4, 3, 1.0, 1.0, lambda x, y: 10.0)
+    _patch_dim(good, bad, "y", ylen)
+    _patch_dim(bad, bad, "x", xlen)
+    with pytest.raises(_capi.MantarayError) as e:
+        _capi.Nc3Reader(bad)
+    assert e.value.code == -5 and "larger than the file" in e.value.message
+    with pytest.raises(_capi.MantarayError) as e:                # the path ray_tracing takes
+        _capi.Fields.open_netcdf3(bad, None)
+    assert e.value.code == -5
+
+
+def test_truncated_data_section_is_a_format_error(tmp_path):
+    good, bad = tmp_path / "good.nc", tmp_path / "bad.nc"
+    create_netcdf3_bathymetry(good, 40, 30, 1.0, 1.0, lambda x, y: 10.0)
+    raw = open(good, "rb").read()
+    open(bad, "wb").write(raw[: len(raw) - 1000])
+    with pytest.raises(_capi.MantarayError) as e:
+        _capi.Nc3Reader(bad)
+    assert e.value.code == -5
+
+
+def test_record_variable_claiming_too_many_records_is_a_format_error(tmp_path):
+    """numrecs is a header field too: 2^31 records of a 16-byte record do not fit in a 150-byte file."""
+    import struct
+
+    p = tmp_path / "rec.nc"
+    name = lambda s: struct.pack(">I", len(s)) + s.encode() + b"\0" * (-len(s) % 4)
+    hdr = b"CDF\x01" + struct.pack(">I", 1 << 31)                       # numrecs
+    hdr += struct.pack(">II", 0x0A, 2) + name("t") + struct.pack(">I", 0) + name("n") + struct.pack(">I", 2)
+    hdr += struct.pack(">II", 0, 0)
+    var = name("v") + struct.pack(">I", 2) + struct.pack(">II", 0, 1) + struct.pack(">II", 0, 0) + struct.pack(">II", 6, 16)
+    hdr += struct.pack(">II", 0x0B, 1) + var
+    begin = len(hdr) + 4
+    open(p, "wb").write(hdr + struct.pack(">I", begin) + b"\0" * 32)
+    with pytest.raises(_capi.MantarayError) as e:
+        _capi.Nc3Reader(p)
+    assert e.value.code == -5 and "records" in e.value.message
+    # the same file with an honest record count reads
+    raw = bytearray(open(p, "rb").read())
+    raw[4:8] = struct.pack(">I", 2)
+    open(p, "wb").write(bytes(raw))
+    with _capi.Nc3Reader(p) as f:
+        assert f.info("v") == (6, 4, (2, 2)) and f.read_f64("v").tolist() == [0.0] * 4

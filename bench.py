@@ -78,8 +78,8 @@ def parse():
     ap.add_argument("--math", default="fast", choices=["fast", "strict"])
     ap.add_argument("--deep-map", default="auto", choices=["auto", "on", "off"],
                     help="depth-floor map of the fast path (mr_trace_opts.flags): the library's own choice, forced on, forced off")
-    ap.add_argument("--same-grid", default="auto", choices=["auto", "off"],
-                    help="same-grid shortcut of the fast path: the library's own choice, or MR_OPT_NO_SAME_GRID")
+    ap.add_argument("--same-grid", default="off", choices=["off", "on"],
+                    help="same-grid shortcut of the fast path (MR_OPT_SAME_GRID, opt-in)")
     ap.add_argument("--shard", default="auto", choices=["auto", "block", "interleave"],
                     help="how the ensemble is shared out over the ranks: one contiguous block each, or tiles dealt round-robin "
                          "(auto: interleave for C5, whose period bands differ in work; block otherwise)")
@@ -376,8 +376,8 @@ def main():
     sm_count = torch.cuda.get_device_properties(local).multi_processor_count
     flush_buf = [None]
     flags = {"auto": 0, "on": _abi.MR_OPT_DEEP_MAP, "off": _abi.MR_OPT_NO_DEEP_MAP}[args.deep_map]
-    if args.same_grid == "off":
-        flags |= _abi.MR_OPT_NO_SAME_GRID
+    if args.same_grid == "on":
+        flags |= _abi.MR_OPT_SAME_GRID
 
     def run_workload(name, steps, warmup, rays_per_gpu, sampler=None):
         """Times `steps` device-resident passes of workload `name` on this rank's share, after `warmup` untimed ones.
@@ -464,7 +464,7 @@ def main():
         kname = "mr::trace_kernel<GRID,GRID,%s>" % ",".join(variant)
         hw, traffic = None, None
         cap = hw_counters.get(wl.name)
-        if cap and args.math == "fast" and bool(cap.get("deep_map")) == deep_map_used and args.same_grid == "auto":
+        if cap and args.math == "fast" and bool(cap.get("deep_map")) == deep_map_used and args.same_grid == "off":
             # the hardware's own count of the same kernel, from the committed ncu capture (a smaller launch of the same
             # shape; per-cycle rates do not depend on the launch size)
             fpc = cap["dadd_per_cycle"] + cap["dmul_per_cycle"] + 2.0 * cap["dfma_per_cycle"]

@@ -8,7 +8,7 @@ runs as hand-written sm_100a CUDA kernels behind the C ABI of
 library, calling into it does (and fails loudly when it is missing).
 """
 
-from ._abi import MR_MATH_FAST, MR_MATH_STRICT, MR_OPT_DEEP_MAP, MR_OPT_NO_DEEP_MAP, MR_OPT_NO_SAME_GRID
+from ._abi import MR_MATH_FAST, MR_MATH_STRICT, MR_OPT_DEEP_MAP, MR_OPT_NO_DEEP_MAP, MR_OPT_SAME_GRID
 from ._capi import (Fields, ManyRays, MantarayError, RayState, SingleRay, TraceResult, depth_floor_map, sample_fields,
                     trace_many)
 from ._mantaray import cache_info, clear_cache
@@ -21,5 +21,5 @@ __all__ = [
     "ManyRays", "SingleRay", "RayState", "Fields", "TraceResult", "trace_many", "sample_fields", "depth_floor_map",
     "MantarayError",
     "ConstantDepth", "ConstantSlope", "CartesianNetcdf3", "ArrayDepth", "ConstantCurrent", "CartesianCurrent",
-    "MR_MATH_FAST", "MR_MATH_STRICT", "MR_OPT_DEEP_MAP", "MR_OPT_NO_DEEP_MAP", "MR_OPT_NO_SAME_GRID",
+    "MR_MATH_FAST", "MR_MATH_STRICT", "MR_OPT_DEEP_MAP", "MR_OPT_NO_DEEP_MAP", "MR_OPT_SAME_GRID",
 ]

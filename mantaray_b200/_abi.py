@@ -72,7 +72,7 @@ class CurrentDesc(C.Structure):
 
 MR_OPT_DEEP_MAP = 1
 MR_OPT_NO_DEEP_MAP = 2
-MR_OPT_NO_SAME_GRID = 4
+MR_OPT_SAME_GRID = 4
 
 
 class TraceOpts(C.Structure):

@@ -473,7 +473,7 @@ static int enqueue_trace(const DeviceFields &d, cudaStream_t stream, int64_t n,
     a.x = x; a.y = y; a.kx = kx; a.ky = ky; a.ld = ld;
     a.rows = rows; a.len = len; a.fin = fin;
     a.deep_map = want_deep_map(d, o);
-    a.same_grid = !(o.flags & MR_OPT_NO_SAME_GRID);
+    a.same_grid = (o.flags & MR_OPT_SAME_GRID) != 0;
     cudaError_t e;
     if (o.math == MR_MATH_STRICT) e = launch_trace_strict(a, stream);
     else if (o.math == MR_MATH_FAST) e = launch_trace_fast(a, stream);
@@ -681,7 +681,7 @@ static int trace_slabs_on_device(DeviceFields &d, const HostJob &j, SlabQueue &q
                 a.ld = chunk;
                 a.rows = B.rows; a.len = B.len; a.fin = B.fin;
                 a.deep_map = want_deep_map(d, j.o);
-                a.same_grid = !(j.o.flags & MR_OPT_NO_SAME_GRID);
+                a.same_grid = (j.o.flags & MR_OPT_SAME_GRID) != 0;
                 // fin is [4][n] with n = m for the kernel (it uses a.n as the pitch)
                 cudaError_t e = j.o.math == MR_MATH_STRICT ? launch_trace_strict(a, s_comp) : launch_trace_fast(a, s_comp);
                 if (e != cudaSuccess) { rc = bail(MR_ERR_CUDA, std::string("trace kernel launch: ") + cudaGetErrorString(e)); goto done; }

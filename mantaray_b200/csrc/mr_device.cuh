@@ -32,6 +32,19 @@ namespace mr {
 // experiment knob: with the same-grid shortcut, hand the current's cell geometry to the bathymetry lookup
 // (saves ~14 instructions per shallow evaluation, costs the registers that keep it alive)
 // experiment knob: deep lanes of the depth-floor map take the fourth-root form (no k, no direction cosines)
+// experiment knobs: one higher-order correction step instead of two second-order ones (sqrt/rsqrt, reciprocal), the
+// exponential's polynomial as two interleaved Horner chains
+// (MR_LEAN_SQRT bit mask: 1 = sqrt(G k tanh kh) of the general wave terms, 2 = sqrt(G k) of the deep-water branch,
+// 4 = k = sqrt(k^2) of the kernels without the depth-floor map)
+#ifndef MR_LEAN_SQRT
+#define MR_LEAN_SQRT 3
+#endif
+#ifndef MR_LEAN_RCP
+#define MR_LEAN_RCP 1
+#endif
+#ifndef MR_EXP_2CHAIN
+#define MR_EXP_2CHAIN 1
+#endif
 #ifndef MR_DEEP_ROOT4
 #define MR_DEEP_ROOT4 1
 #endif
@@ -44,8 +57,9 @@ namespace mr {
 #ifndef MR_DMAP_LATE_LOAD
 #define MR_DMAP_LATE_LOAD 1
 #endif
+// (bit mask: 1 = the plain kernel, 2 = the depth-floor-map kernels, 4 = the same-grid kernel without the map)
 #ifndef MR_EARLY_GRAD
-#define MR_EARLY_GRAD 1
+#define MR_EARLY_GRAD 4
 #endif
 #ifndef MR_SG_SHARE_GEOM
 #define MR_SG_SHARE_GEOM 1
@@ -446,47 +460,62 @@ __device__ __forceinline__ void rhs_f64_strict(double kx, double ky, double h, d
 // For normal, positive, finite arguments (what the path produces when `ok`); other
 // inputs give NaN/garbage that the caller replaces.
 
-// sqrt(x) and 1/sqrt(x) together: MUFU.RSQ64H seed (~2^-23) + two coupled
-// Goldschmidt steps -> both within ~1 ulp.
+// sqrt(x) and 1/sqrt(x) together: MUFU.RSQ64H seed y0 (within ~2^-20) and ONE fourth-order step.  With
+// e = 1 - x y0^2 the exact value is y0 (1 - e)^(-1/2) = y0 (1 + e/2 + 3 e^2/8 + 5 e^3/16 + ...); the first omitted
+// term is 0.27 e^4 < 2^-80.  1/sqrt within 1 ulp, sqrt = x / sqrt(x) within 1.5 ulp.  Eight operations, six deep
+// (two coupled Goldschmidt steps were ten and seven).
+template <bool LEAN = false>
 __device__ __forceinline__ void sqrt_rsqrt(double x, double &s, double &rs)
 {
     double y0;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
-    double g = x * y0, hh = 0.5 * y0;
+  if (LEAN) {
+    const double e = fma(-x, y0 * y0, 1.0);
+    const double p = fma(e, fma(e, 0.3125, 0.375), 0.5);
+    rs = fma(y0 * e, p, y0);
+    s = x * rs;
+  } else {
+    double g = x * y0, hh = 0.5 * y0;              // two coupled Goldschmidt steps
     double r = fma(-g, hh, 0.5);
     g = fma(g, r, g); hh = fma(hh, r, hh);
     r = fma(-g, hh, 0.5);
     g = fma(g, r, g); hh = fma(hh, r, hh);
     s = g; rs = hh + hh;
+  }
 }
 
-// 1/x: MUFU.RCP64H seed + two Newton steps
+// 1/x: MUFU.RCP64H seed r0 and one third-order step: with e = 1 - x r0, 1/x = r0 (1 + e + e^2 + ...), e^3 < 2^-60
 __device__ __forceinline__ double recip(double x)
 {
     double r0;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(x));
-    double e = fma(-x, r0, 1.0);
+#if MR_LEAN_RCP
+    const double e = fma(-x, r0, 1.0);
+    return fma(fma(e, e, e), r0, r0);
+#else
+    double e = fma(-x, r0, 1.0);                   // two Newton steps
     r0 = fma(r0, e, r0);
     e = fma(-x, r0, 1.0);
     return fma(r0, e, r0);
+#endif
 }
 
 // x^(-1/4) for a normal, positive, finite x: three MUFU seeds (x^-1/2, its own inverse square root x^1/4, the
-// reciprocal of that: ~2^-20 together) and two Newton steps t += t (1 - x t^4) / 4 (error e -> 2.5 e^2) -> ~2 ulp.
-// x = +inf gives NaN (0 * inf in the residual), NaN gives NaN.
+// reciprocal of that: within ~2^-18 together) and ONE fourth-order step.  With e = 1 - x t^4 the exact root is
+// t (1 - e)^(-1/4) = t (1 + e/4 + 5 e^2/32 + 15 e^3/128 + ...); the first omitted term is 0.1 e^4 < 2^-67, and the
+// rounding of e (an fma on t^4, itself two roundings) enters scaled by t/4: the result is within 1 ulp (checked
+// against 80-bit arithmetic for seeds off by up to 2^-17).  Seven operations, six deep, against ten and eight for
+// two Newton steps.  x = +inf gives NaN (0 * inf in the residual), x = 0 gives NaN (inf * 0), NaN gives NaN.
 __device__ __forceinline__ double inv_root4(double x)
 {
     double y, s, t;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(s) : "d"(y));
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(t) : "d"(s));
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const double t2 = t * t;
-        const double e = fma(-x, t2 * t2, 1.0);
-        t = fma(0.25 * t, e, t);
-    }
-    return t;
+    const double t2 = t * t;
+    const double e = fma(-x, t2 * t2, 1.0);
+    const double p = fma(e, fma(e, 0.1171875, 0.15625), 0.25);
+    return fma(t * e, p, t);
 }
 
 // E = exp(z) and em = expm1(z) for z in [-44, 0] (larger kh takes the deep-water branch).
@@ -500,10 +529,20 @@ __device__ __forceinline__ void exp_expm1_neg(double z, double &E, double &em)
     double nd = t - MAGIC;
     double r = fma(-nd, kExpRed[2], z);
     r = fma(-nd, kExpRed[3], r);
+#if MR_EXP_2CHAIN
+    // P(r) = c0 r^11 + ... + c11 as two Horner chains in r^2 (odd and even coefficients), half as deep as one
+    const double r2 = r * r;
+    double po = kExpm1C[0], pe = kExpm1C[1];
+#pragma unroll
+    for (int i = 2; i < 12; i += 2) { po = fma(po, r2, kExpm1C[i]); pe = fma(pe, r2, kExpm1C[i + 1]); }
+    double p = fma(po, r, pe);
+    p = fma(r2, p, r);                             // expm1(r)
+#else
     double p = kExpm1C[0];
 #pragma unroll
     for (int i = 1; i < 12; ++i) p = fma(p, r, kExpm1C[i]);
     p = fma(r * r, p, r);                          // expm1(r)
+#endif
     double s = __hiloint2double((n + 1023) << 20, 0);   // 2^n, n in [-64, 0]
     E = fma(s, p, s);
     em = fma(s, p, s - 1.0);
@@ -536,7 +575,7 @@ __device__ __forceinline__ void wave_terms(double k, double h, double dhdx, doub
         const double csch_sech = E4 * r;
         const double q = (k * kExpRed[5]) * T;
         double sq, rq;
-        sqrt_rsqrt(q, sq, rq);
+        sqrt_rsqrt<(MR_LEAN_SQRT & 1) != 0>(q, sq, rq);
         cg = kExpRed[6] * ((T + hs2) * rq);
         const double Bc = ((-0.5 * k) * csch_sech) * sq;
         bx = Bc * dhdx; by = Bc * dhdy;
@@ -550,7 +589,7 @@ __device__ __forceinline__ void wave_terms(double k, double h, double dhdx, doub
         // and propagates a non-finite gradient.
         const double z = kh * 0.0, zk = k * 0.0;
         double sq, rq;
-        sqrt_rsqrt(k * kExpRed[5], sq, rq);
+        sqrt_rsqrt<(MR_LEAN_SQRT & 2) != 0>(k * kExpRed[5], sq, rq);
         cg = fma(kExpRed[6], rq, z);
         bx = -zk * dhdx; by = -zk * dhdy;
     }
@@ -592,7 +631,9 @@ template <int BK, int CK, bool UNI, bool DMAP = false, bool SG = false>
 struct FastRay {
     static constexpr bool kDmap = DMAP && UNI && BK == MR_BATHY_GRID;
     static constexpr bool kSame = SG && UNI && BK == MR_BATHY_GRID && CK == MR_CURRENT_GRID;
-    static constexpr bool kEarly = MR_EARLY_GRAD && CK == MR_CURRENT_GRID;     // advection sums formed ahead of the bilinears
+    // advection sums formed ahead of the bilinears: in the variants that need the registers (measured: the plain
+    // kernel is 8 % slower with it, 63.9 -> 69.2 ms on C4)
+    static constexpr bool kEarly = CK == MR_CURRENT_GRID && ((MR_EARLY_GRAD & 1) && !kDmap && !kSame || (MR_EARLY_GRAD & 2) && kDmap && !kSame || (MR_EARLY_GRAD & 4) && kSame);
     static constexpr bool kShare = kSame && !kDmap && MR_SG_SHARE_GEOM;      // one cell geometry for both lookups (with the map the depth lookup is the rare path)
     float xf, yf;
     bool ok;
@@ -605,7 +646,7 @@ struct FastRay {
     float4 Z, U, V;
     double2 gh, gu, gv;
     float bxa, bxb, bya, byb, cxa, cxb, cya, cyb;
-    double k2, k, cs, sn;      // deep lanes of the depth-floor map: k holds (sqrt(G)/2) k^-3/2, cs holds k2 * 0
+    double k2, k, cs, sn;      // with the depth-floor map k holds t = k^-1/2 from phase 3 until phase 4
     double ax, ay;             // kEarly: -kx du/dx - ky dv/dx, -kx du/dy - ky dv/dy
 
     // f64 fractional index of the current and its cell (cartesian_current.rs:246-252).  The spacing is a launch
@@ -679,6 +720,17 @@ struct FastRay {
         return true;
     }
 
+    // With the depth-floor map nothing of the bathymetry's cell is carried through the deep lanes' path: a lane that
+    // does need the depth derives its cell again from (xf, yf) — the operations of phase 1
+    __device__ __forceinline__ void bathy_cell_again(const BathyDev &b)
+    {
+        const f32x2 t = sub2(pk(xf, yf), b.p0);
+        f32x2 q = mul2(t, b.rs2);
+        q = fma2(fma2(q, b.ns2, t), b.rs2, q);
+        q = fma2(fma2(q, b.ns2, t), b.rs2, q);
+        bx1 = cell_of(lo_of(q), b.nx); by1 = cell_of(hi_of(q), b.ny);
+    }
+
     // ---- phase 2: all record loads -----------------------------------------------------------------
     __device__ __forceinline__ void phase2(const BathyDev &b, const CurrentDev &c)
     {
@@ -686,7 +738,7 @@ struct FastRay {
             if (kDmap) {
                 // (a NaN or infinite k^2 fails or passes harmlessly: NaN compares false; k^2 = inf makes k NaN,
                 // and the deep-water branch turns that into four NaNs like the general one)
-                deep = ok && __fmul_rn((float)k2, hsq) >= 484.01f;
+                if (!(MR_DEEP_ROOT4 && MR_DMAP_LATE_LOAD)) deep = ok && __fmul_rn((float)k2, hsq) >= 484.01f;
                 if (!MR_DMAP_LATE_LOAD) ldg_f4_d2_unless(deep, brec, Z, gh);
             } else {
                 ldg_f4_d2(brec, Z, gh);
@@ -707,19 +759,21 @@ struct FastRay {
     }
 
     // ---- phase 3: wavenumber-only f64 work, under the loads --------------------------------------
+    // With the depth-floor map everything is derived from ONE fourth root, t = (k^2)^-1/4 = k^-1/2, whichever way
+    // the lane goes afterwards — so nothing here waits for the map's answer, whose load is still in flight:
+    //   proven deep:  cg cos(theta) = (G/2) / sqrt(G k) * kx / k = (sqrt(G)/2) t^3 kx, likewise sin; k is never formed;
+    //   otherwise:    1/k = t^2, k = k^2 t^2, and the general wave terms as without the map.
     __device__ __forceinline__ void phase3(double kx, double ky)
     {
-        if (MR_DEEP_ROOT4 && kDmap && deep) {
-            // Proven deep water: cg = (G/2) / sqrt(G k) and the direction cosines kx/k, ky/k only ever appear as
-            // cg kx / k = (sqrt(G)/2) k^-3/2 kx.  One fourth root of k^2 gives k^-1/2; k itself is never formed.
-            // k2 * 0 carries an infinite k^2 into every output as NaN, like the general branch (see wave_terms).
-            const double t = inv_root4(k2);
-            k = (t * t) * (t * kExpRed[7]);
-            cs = k2 * 0.0;
+        if (MR_DEEP_ROOT4 && kDmap) {
+            k = inv_root4(k2);             // t, until phase 4
+            // the map's answer is consumed only now, behind the fourth root's chain (a warp issues in order: the
+            // first instruction that needs the loaded value is where it waits)
+            if (MR_DMAP_LATE_LOAD) deep = ok && __fmul_rn((float)k2, hsq) >= 484.01f;
             return;
         }
         double rk;
-        sqrt_rsqrt(k2, k, rk);
+        sqrt_rsqrt<(MR_LEAN_SQRT & 4) != 0>(k2, k, rk);
         cs = kx * rk; sn = ky * rk;
     }
 
@@ -848,8 +902,11 @@ struct FastRay {
                 return;
             }
             if (deep) {
-                // k = (sqrt(G)/2) k^-3/2, cs = k2 * 0 (phase3): cg cos = k kx, cg sin = k ky, bathymetric term -0
-                const double w = k, z = cs;
+                // cg cos = w kx, cg sin = w ky with w = (sqrt(G)/2) k^-3/2; the bathymetric term is -0, and k2 * 0
+                // carries an infinite k^2 into the wavenumber derivatives as NaN, like the general branch (see
+                // wave_terms; w itself is NaN then: inv_root4)
+                const double t = k;
+                const double w = (t * t) * (t * kExpRed[7]), z = k2 * 0.0;
                 out[0] = fma(w, kx, cv.u);          // (an infinite k^2 has already turned w into NaN: inv_root4)
                 out[1] = fma(w, ky, cv.v);
                 if (kEarly) {
@@ -861,10 +918,20 @@ struct FastRay {
                 }
                 return;
             }
+            if (MR_DEEP_ROOT4) {               // not proven deep: 1/k = t^2, k = k^2 / k, direction cosines
+                const double rk = k * k;
+                k = k2 * rk;
+                cs = kx * rk; sn = ky * rk;
+            }
             double cg, bx, by;
             float h32;
             double dhdx, dhdy;
-            if (MR_DMAP_LATE_LOAD) ldg_f4_d2(brec, Z, gh);
+            if (MR_DMAP_LATE_LOAD) {
+                // the lanes that need the depth after all: cell, record address and the record itself, now
+                if (!kSame) bathy_cell_again(b);
+                brec = b.cell + 2u * (unsigned)((b.nx - 1) * by1 + bx1);
+                ldg_f4_d2(brec, Z, gh);
+            }
             bathy_part(b, p, h32, dhdx, dhdy, kShare ? &g : nullptr);
             ok = ok && h32 > 0.0f;
             wave_terms(k, (double)(ok ? h32 : qnanf()), dhdx, dhdy, cg, bx, by);

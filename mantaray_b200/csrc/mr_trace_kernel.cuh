@@ -40,7 +40,7 @@ struct TraceArgs {
     int32_t *rows, *len;       // [n] or NULL
     double *fin;               // [4][n] or NULL
     int32_t deep_map;          // use the bathymetry's depth-floor map where the grids allow it (MR_OPT_DEEP_MAP)
-    int32_t same_grid;         // use the same-grid shortcut where the grids allow it (off: MR_OPT_NO_SAME_GRID)
+    int32_t same_grid;         // use the same-grid shortcut where the grids allow it (MR_OPT_SAME_GRID)
     // filled by launch_trace_math: the trajectory planes as byte offsets from the x plane, the row pitch in bytes
     int64_t off_y, off_kx, off_ky, row_bytes;
     double sixth;              // dt / 6 (read from here by the depth-floor-map variant, which is short of registers)
@@ -61,11 +61,17 @@ static constexpr int kBlock = kBlockThreads;
 #ifndef MR_K0_TEST
 #define MR_K0_TEST 1
 #endif
+#ifndef MR_FIN_SHADOW
+#define MR_FIN_SHADOW 0
+#endif
 #ifndef MR_ROW_POINTER
 #define MR_ROW_POINTER 1
 #endif
 #ifndef MR_Y_SHARED
 #define MR_Y_SHARED 0
+#endif
+#ifndef MR_ACC_SHARED
+#define MR_ACC_SHARED 0
 #endif
 // grids whose f32 coordinates are not affine keep the per-cell corner coordinates and basis live: more registers
 #ifndef MR_MIN_BLOCKS_GENERIC
@@ -132,6 +138,9 @@ trace_kernel(const __grid_constant__ TraceArgs a)
     // live through every right-hand side; it is read once per stage and written once per step.
     constexpr bool kYsh = MR_Y_SHARED && MATH == MR_MATH_FAST;
     __shared__ double ysh[kYsh ? 4 : 1][kYsh ? kBlock : 1];
+    // MR_ACC_SHARED: the RK4 accumulator k0 + 2 k1 + 2 k2 + k3 likewise (read and written once per stage)
+    constexpr bool kAsh = MR_ACC_SHARED && MATH == MR_MATH_FAST;
+    __shared__ double ash[kAsh ? 4 : 1][kAsh ? kBlock : 1];
     double yreg[4];
     auto Y = [&](int c) -> double & { return kYsh ? ysh[c][threadIdx.x] : yreg[c]; };
     auto load_state = [&](double out[4]) {
@@ -140,6 +149,11 @@ trace_kernel(const __grid_constant__ TraceArgs a)
     };
     // MR_ROW_POINTER: the thread carries a pointer to its element of the last stored row; otherwise only the
     // (warp-uniform) row number is carried and the address is formed when a row is stored
+    // MR_FIN_SHADOW: the state before the step is parked in shared memory (each thread its own slots) for the one
+    // event that needs it — the first NaN, when the last NaN-free state is written out — instead of being held in
+    // registers, or spilled to local memory by the compiler, through the update
+    constexpr bool kShadow = MR_FIN_SHADOW && MATH == MR_MATH_FAST && !kYsh;
+    __shared__ double yprev[kShadow ? 4 : 1][kShadow ? kBlock : 1];
     char *p = nullptr;                     // this ray's element of the last stored row of the x plane
     int32_t row = 0;                       // the last stored row
     auto row_ptr = [&]() -> char * {
@@ -165,12 +179,13 @@ trace_kernel(const __grid_constant__ TraceArgs a)
     for (int32_t s = 1; s <= nsteps; ++s) {
         if (!__any_sync(0xffffffffu, alive)) break;
         if (alive) {
-            double k[1][4], acc[4];
+            double k[1][4], accreg[4];
+            auto ACC = [&](int c) -> double & { return kAsh ? ash[c][threadIdx.x] : accreg[c]; };
 #if MR_K0_TEST
             bool k0_nan;
 #endif
 #pragma unroll
-            for (int c = 0; c < 4; ++c) { k[0][c] = 0.0; acc[c] = -0.0; }    // -0 + k0 == k0 for every k0
+            for (int c = 0; c < 4; ++c) { k[0][c] = 0.0; ACC(c) = -0.0; }    // -0 + k0 == k0 for every k0
 #pragma unroll kStageUnroll
             for (int st = 0; st < 4; ++st) {
                 const double as = (st == 0) ? 0.0 : (st == 3 ? dt : half);
@@ -189,14 +204,20 @@ trace_kernel(const __grid_constant__ TraceArgs a)
                 if (st == 0) k0_nan = all_nan4(k[0]);
 #endif
 #pragma unroll
-                for (int c = 0; c < 4; ++c)
-                    acc[c] = (MATH == MR_MATH_STRICT) ? __dadd_rn(acc[c], __dmul_rn(k[0][c], ws)) : fma(k[0][c], ws, acc[c]);
+                for (int c = 0; c < 4; ++c) {
+                    const double ac = ACC(c);
+                    ACC(c) = (MATH == MR_MATH_STRICT) ? __dadd_rn(ac, __dmul_rn(k[0][c], ws)) : fma(k[0][c], ws, ac);
+                }
             }
             double yn[4];
+            if (kShadow && a.fin) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) yprev[c][threadIdx.x] = Y(c);
+            }
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-                const double yc = Y(c);
-                yn[c] = (MATH == MR_MATH_STRICT) ? __dadd_rn(yc, __dmul_rn(acc[c], sixth)) : fma(acc[c], sixth, yc);
+                const double yc = Y(c), ac = ACC(c);
+                yn[c] = (MATH == MR_MATH_STRICT) ? __dadd_rn(yc, __dmul_rn(ac, sixth)) : fma(ac, sixth, yc);
             }
             const bool n0 = isnan(yn[0]), n1 = isnan(yn[1]), n2 = isnan(yn[2]), n3 = isnan(yn[3]);
             if (clean && (n0 || n1 || n2 || n3)) {
@@ -204,7 +225,12 @@ trace_kernel(const __grid_constant__ TraceArgs a)
                 if (a.len) store_count(a, a.len, s);
                 if (a.fin) {                          // the row before this one is the last NaN-free state
                     double yo[4];
-                    load_state(yo);
+                    if (kShadow) {
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) yo[c] = yprev[c][threadIdx.x];
+                    } else {
+                        load_state(yo);
+                    }
                     store_fin(a, yo);
                 }
             }

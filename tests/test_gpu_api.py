@@ -89,6 +89,30 @@ def test_file_entry_point_matches_descriptor_entry_point(gpu, tmp_path):
     np.testing.assert_array_equal(a.x, bb.x)
 
 
+def test_repeated_api_calls_reuse_the_field_handle(gpu, island_and_current):
+    """the second call on the same files skips parse and upload (the reference re-opens both files on
+    every call, src/ffi.rs:62-64); a rewritten file is opened again."""
+    island, current = island_and_current
+    mantaray_b200.clear_cache()
+    base = mantaray_b200.cache_info()
+    a = mantaray.ray_tracing(3 * [-1000], 3 * [0], 3 * [0.01], 3 * [0], 10, 2, str(island), str(current))
+    b = mantaray.ray_tracing(3 * [-1000], 3 * [0], 3 * [0.02], 3 * [0], 10, 2, str(island), str(current))
+    c = mantaray.single_ray(-1000, 0, 0.01, 0, 10, 2, island, current)
+    info = mantaray_b200.cache_info()
+    assert info["misses"] - base["misses"] <= 2 and info["hits"] - base["hits"] >= 1      # ray_tracing twice: one open
+    np.testing.assert_array_equal(np.asarray(a.x)[:, 0], np.asarray(c.x))
+    assert (np.asarray(b.kx) == 0.02).all()
+    # rewrite the bathymetry (shallower): same path, new content -> new handle, new result
+    x = np.array([-1e4, 0.0, 1e4])
+    import time
+    time.sleep(0.02)
+    write_netcdf3(island, [("x", 3), ("y", 3)], {"x": (["x"], x), "y": (["y"], x), "depth": (["x", "y"], 5.0 * np.ones((3, 3)))})
+    d = mantaray.ray_tracing(3 * [-1000], 3 * [0], 3 * [0.01], 3 * [0], 10, 2, str(island), str(current))
+    assert not np.array_equal(np.asarray(d.x), np.asarray(a.x))                  # 5 m of water: slower group velocity
+    mantaray_b200.clear_cache()
+    assert mantaray_b200.cache_info()["entries"] == 0
+
+
 def test_file_errors_raise(gpu, tmp_path):
     with pytest.raises(OSError):
         mantaray.single_ray(0, 0, 0.01, 0, 10, 2, tmp_path / "nope.nc", tmp_path / "nope2.nc")

@@ -4,8 +4,10 @@ deep for a 10 s wave; MR_OPT_DEEP_MAP forces it on, MR_OPT_NO_DEEP_MAP off.  The
 map to the oracle (same bar as everywhere) and to the path WITHOUT it — same rows, same len, same NaN pattern,
 values to a few ulp (a lane the map proves deep evaluates cg cos(theta) as (sqrt(G)/2) k^-3/2 kx from one fourth
 root instead of forming k, 1/k and 1/sqrt(G k): the same function, rounded differently) — on every grid that has
-a map, whatever its deep share.  The same-grid shortcut (MR_OPT_NO_SAME_GRID switches it off) changes no
-operation at all, only which index names the cell: with it and without it the results are bit-identical."""
+a map, whatever its deep share.  The same-grid shortcut (MR_OPT_SAME_GRID switches it on) only changes which
+index names the cell: the cells, hence every looked-up value, are identical; the kernel variants differ in how
+they round the sum of the advection terms, so the comparison is to the same few ulp (a wrong cell would show up
+at 1e-6)."""
 
 import os
 
@@ -52,11 +54,11 @@ def assert_same(mapped, plain, what, exact=False):
 
 
 def same_grid_pair(f, rays, t_end, dt, **kw):
-    """(separate lookups, same-grid shortcut), both without the map: must be bit-identical"""
-    from mantaray_b200._abi import MR_OPT_NO_SAME_GRID
-    sep = trace_many(f, *rays, 0.0, t_end, dt, math=MR_MATH_FAST, final_state=True,
-                     flags=MR_OPT_NO_DEEP_MAP | MR_OPT_NO_SAME_GRID, **kw)
-    sg = trace_many(f, *rays, 0.0, t_end, dt, math=MR_MATH_FAST, final_state=True, flags=MR_OPT_NO_DEEP_MAP, **kw)
+    """(separate lookups, same-grid shortcut), both without the map"""
+    from mantaray_b200._abi import MR_OPT_SAME_GRID
+    sep = trace_many(f, *rays, 0.0, t_end, dt, math=MR_MATH_FAST, final_state=True, flags=MR_OPT_NO_DEEP_MAP, **kw)
+    sg = trace_many(f, *rays, 0.0, t_end, dt, math=MR_MATH_FAST, final_state=True,
+                    flags=MR_OPT_NO_DEEP_MAP | MR_OPT_SAME_GRID, **kw)
     return sep, sg
 
 
@@ -75,7 +77,7 @@ def test_workloads_with_the_depth_floor_map(oracle, gpu, name, make):
         sep, sg = same_grid_pair(f, rays, wl.duration, wl.dt, stride=wl.stride)
     assert_parity(mapped, ref, what=f"{name} with the depth-floor map")
     assert_same(mapped, plain, name)
-    assert_same(sg, sep, f"{name}: same-grid shortcut", exact=True)
+    assert_same(sg, sep, f"{name}: same-grid shortcut")
 
 
 @pytest.mark.parametrize("seed", range(int(os.environ.get("MR_FUZZ_SEEDS", "120"))))
@@ -88,7 +90,7 @@ def test_fuzz_with_the_depth_floor_map(oracle, gpu, seed):
         sep, sg = same_grid_pair(f, rays, dt * steps, dt, stride=stride)
     assert_parity(mapped, ref, what=f"fuzz seed {seed} with the depth-floor map")
     assert_same(mapped, plain, f"fuzz seed {seed}")
-    assert_same(sg, sep, f"fuzz seed {seed}: same-grid shortcut", exact=True)
+    assert_same(sg, sep, f"fuzz seed {seed}: same-grid shortcut")
 
 
 def test_blocks_with_dry_and_non_finite_nodes_fall_back_to_the_lookup(oracle, gpu):
@@ -122,7 +124,7 @@ def test_blocks_with_dry_and_non_finite_nodes_fall_back_to_the_lookup(oracle, gp
             sep, sg = same_grid_pair(f, (x0, y0, kx0, ky0), dt * steps, dt)
         assert_parity(mapped, ref, what="dry / non-finite blocks with the depth-floor map")
         assert_same(mapped, plain, "dry / non-finite blocks")
-        assert_same(sg, sep, "dry / non-finite blocks: same-grid shortcut", exact=True)
+        assert_same(sg, sep, "dry / non-finite blocks: same-grid shortcut")
 
 
 def test_default_follows_the_deep_share_of_the_grid(gpu):

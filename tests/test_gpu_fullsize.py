@@ -117,3 +117,61 @@ def test_c1_canonical_through_the_python_api(oracle, gpu, tmp_path):
     assert np.abs(x[:, sel] - ref.x).max() <= REL_TOL * scale
     assert np.abs(np.asarray(ds.y)[:, sel] - ref.y).max() <= REL_TOL * scale
     np.testing.assert_array_equal(np.asarray(ds.time)[:, 0], ref.t)
+
+
+def test_c4_agulhas_1m_rays_full_trajectories(oracle, gpu):
+    """configs[3], the benchmarked configuration, laid out exactly as bench.py lays it out: 1M rays x 2049 rows,
+    four 16.4 GB planes in one device buffer (ld = 1 000 000, plane offsets beyond 2^34 bytes, 7 813 blocks),
+    written by ONE mr_trace_device launch with the library's default flags.  2 049 strided columns plus every
+    rows / len / final state come back and are held to the oracle: termination bit-exact, trajectories to 1e-9."""
+    import ctypes as C
+
+    import torch
+
+    from mantaray_b200 import _abi, _capi
+
+    free_b, _ = torch.cuda.mem_get_info(0)
+    if free_b < 70e9:
+        pytest.skip("needs 66 GB of free device memory")
+    lib = _capi.load()
+    wl = W.c4_agulhas()
+    n, rows = wl.n_rays, wl.n_rows
+    assert (n, rows) == (1_000_000, 2049)
+    x0, y0, kx0, ky0 = wl.all_rays()
+    dev = torch.device("cuda", 0)
+    ic = torch.from_numpy(np.stack([x0, y0, kx0, ky0])).to(dev)
+    traj = torch.empty((4, rows, n), dtype=torch.float64, device=dev)
+    traj.fill_(-1.0)                                    # any element the launch fails to write shows up
+    d_rows = torch.empty(n, dtype=torch.int32, device=dev)
+    d_len = torch.empty(n, dtype=torch.int32, device=dev)
+    d_fin = torch.empty((4, n), dtype=torch.float64, device=dev)
+    p = lambda t: C.c_void_p(t.data_ptr())
+    st = torch.cuda.current_stream()
+    with Fields(wl.bathymetry, wl.current, devices=[0]) as f:
+        rc = lib.mr_trace_device(f.handle, 0, C.c_void_p(st.cuda_stream), n, p(ic[0]), p(ic[1]), p(ic[2]), p(ic[3]),
+                                 0.0, wl.duration, wl.dt, None, p(traj[0]), p(traj[1]), p(traj[2]), p(traj[3]), n,
+                                 p(d_rows), p(d_len), p(d_fin), None)
+        assert rc == 0, lib.mr_last_error()
+        torch.cuda.synchronize()
+    sel = np.unique(np.linspace(0, n - 1, 2049).astype(np.int64))
+    sel = np.union1d(sel, [0, 1, 127, 128, n - 129, n - 128, n - 2, n - 1])      # first / last block and warp edges
+    sel_t = torch.from_numpy(sel).to(dev)
+
+    class Got:
+        pass
+
+    got = Got()
+    got.rows, got.len = d_rows[sel_t].cpu().numpy(), d_len[sel_t].cpu().numpy()
+    got.x, got.y, got.kx, got.ky = (traj[i][:, sel_t].cpu().numpy() for i in range(4))
+    ref = oracle.trace_many(wl.bathymetry, wl.current, x0[sel], y0[sel], kx0[sel], ky0[sel], 0.0, wl.duration, wl.dt)
+    worst = assert_parity(got, ref, what="C4 at the benchmark's size and layout")
+    assert worst <= REL_TOL
+    _final_state_close(d_fin[:, sel_t].cpu().numpy(), ref.final_state)
+    # whole-batch invariants: every row of every plane was written (no sentinel left), rows beyond a ray's own
+    # are NaN, and the executed ray-steps are the number bench.py divides by
+    rows_all = d_rows.to(torch.int64)
+    assert int((traj == -1.0).sum().item()) == 0
+    last = traj[0][rows - 1]
+    assert bool(torch.isnan(last)[rows_all < rows].all().item())
+    assert int((rows_all - 1).sum().item()) == int((d_rows.cpu().numpy().astype(np.int64) - 1).sum())
+    assert bool((d_len.to(torch.int64) <= rows_all).all().item()) and int(rows_all.max().item()) == rows

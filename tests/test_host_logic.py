@@ -207,3 +207,53 @@ def test_interleaved_tiles_cover_the_batch_once_and_mix_the_periods():
                 assert periods == set(range(wl.extra["n_periods"])), (world, r, periods)
         assert (seen == 1).all()
     assert W.shard_tiles(10, 1, 4, 3) == [(3, 6)] and W.shard_tiles(10, 3, 4, 3) == [(9, 10)] and W.shard_tiles(5, 2, 4, 3) == []
+
+
+def test_field_handle_cache_keys_on_the_files_and_evicts(tmp_path, monkeypatch):
+    """repeated API calls on the same files reuse one field handle; a rewritten file, another
+    device set or a full cache get a new one; clear_cache() frees everything.  (Handle creation is stubbed: no GPU.)"""
+    import time
+
+    made, freed, trimmed = [], [], []
+
+    class FakeFields:
+        def __init__(self, key):
+            self.key = key
+            made.append(key)
+
+        def free(self):
+            freed.append(self.key)
+
+        def trim(self):
+            trimmed.append(self.key)
+
+    monkeypatch.setattr(_capi.Fields, "open_netcdf3", classmethod(lambda cls, b, c, devices=None: FakeFields((b, c, tuple(devices)))))
+    monkeypatch.setenv("MANTARAY_B200_CACHE", "2")
+    _mantaray.clear_cache()
+    b, c, b2 = tmp_path / "b.nc", tmp_path / "c.nc", tmp_path / "b2.nc"
+    for p in (b, c, b2):
+        p.write_bytes(b"x" * 10)
+    base = _mantaray.cache_info()
+    with _mantaray._open_fields(str(b), str(c), [0]) as f1:
+        pass
+    with _mantaray._open_fields(str(b), str(c), [0]) as f2:
+        pass
+    assert f1 is f2 and len(made) == 1 and not freed                      # reused, not freed on exit
+    info = _mantaray.cache_info()
+    assert (info["hits"] - base["hits"], info["misses"] - base["misses"], info["entries"]) == (1, 1, 1)
+    with _mantaray._open_fields(str(b), str(c), [0, 1]) as f3:             # another device set: another handle
+        pass
+    assert f3 is not f1 and trimmed == [f1.key]                            # only the newest keeps its work buffers
+    time.sleep(0.01)
+    b.write_bytes(b"y" * 11)                                               # rewritten file: new key, oldest entry evicted
+    with _mantaray._open_fields(str(b), str(c), [0]) as f4:
+        pass
+    assert f4 is not f1 and freed == [f1.key] and _mantaray.cache_info()["entries"] == 2
+    with pytest.raises(OSError):
+        _mantaray._open_fields(str(tmp_path / "missing.nc"), str(c), [0])
+    _mantaray.clear_cache()
+    assert _mantaray.cache_info()["entries"] == 0 and len(freed) == 3
+    monkeypatch.setenv("MANTARAY_B200_CACHE", "0")                         # disabled: a private handle, freed on exit
+    with _mantaray._open_fields(str(b2), str(c), [0]) as f5:
+        pass
+    assert freed[-1] == f5.key and _mantaray.cache_info()["entries"] == 0

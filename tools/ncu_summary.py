@@ -1,10 +1,13 @@
 #!/usr/bin/env python
 """Summarise an .ncu-rep: the metrics the profiles/ tables quote, and the executed opcode mix.
 
-    python tools/ncu_summary.py report.ncu-rep [out_prefix]
+    python tools/ncu_summary.py report.ncu-rep [out_prefix] [--hw hw_counters.json WORKLOAD RAYS WARP_RHS [traffic.csv TRAFFIC_RAYS STEPS]]
 
-Writes <prefix>_ncu_summary.txt and <prefix>_opcode_mix.txt (needs `ncu` on PATH; no GPU)."""
-import collections, csv, io, re, subprocess, sys
+Writes <prefix>_ncu_summary.txt and <prefix>_opcode_mix.txt (needs `ncu` on PATH; no GPU).  With --hw it also
+records the hardware-counted figures bench.py quotes beside the algorithmic roofline (roofline.hw) under WORKLOAD
+in hw_counters.json: FP64 instructions per cycle, pipe utilisations, instructions per RHS (executed warp
+instructions / WARP_RHS of the captured launch) and, if given, the DRAM bytes of a full-size launch."""
+import collections, csv, io, json, os, re, subprocess, sys
 
 METRICS = """dram__bytes_read.sum dram__bytes_write.sum gpu__time_duration.sum l1tex__t_sector_hit_rate.pct
 launch__registers_per_thread lts__t_sector_hit_rate.pct sm__cycles_elapsed.avg sm__cycles_elapsed.avg.per_second
@@ -50,10 +53,58 @@ def source(rep):
     return static, mix, samples
 
 
+def metric(vals, name):
+    key = next((k for k in vals if k == name or k.endswith("." + name)), None)
+    return float(vals[key][1].replace(",", "")) if key and vals[key][1] != "" else None
+
+
+def template_flag(kernel, i):
+    """trace_kernel<BK, CK, MATH, UNI, DMAP, SG>: parameter i as a bool (None if the name has no such parameter)"""
+    m = re.search(r"<([^>]*)>", kernel)
+    p = [t.strip() for t in m.group(1).split(",")] if m else []
+    return (p[i] in ("1", "true")) if i < len(p) else None
+
+
+def record_hw(vals, kernel, rep, args):
+    path, workload, rays, warp_rhs = args[0], args[1], int(args[2]), float(args[3])
+    db = {}
+    if os.path.exists(path):
+        db = json.load(open(path))
+    inst = metric(vals, "smsp__inst_executed.sum")
+    e = {
+        "kernel": kernel, "capture": os.path.basename(rep) + " (ncu --set full --clock-control none), summarised in profiles/",
+        "rays": rays, "deep_map": template_flag(kernel, 4), "same_grid": template_flag(kernel, 5),
+        "pipe_fp64_pct": metric(vals, "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"),
+        "dadd_per_cycle": metric(vals, "smsp__sass_thread_inst_executed_op_dadd_pred_on.sum.per_cycle_elapsed"),
+        "dmul_per_cycle": metric(vals, "smsp__sass_thread_inst_executed_op_dmul_pred_on.sum.per_cycle_elapsed"),
+        "dfma_per_cycle": metric(vals, "smsp__sass_thread_inst_executed_op_dfma_pred_on.sum.per_cycle_elapsed"),
+        "issue_active_pct": metric(vals, "sm__issue_active.avg.pct_of_peak_sustained_elapsed"),
+        "l1_lsu_wavefronts_pct": metric(vals, "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"),
+        "registers": metric(vals, "launch__registers_per_thread"),
+        "instr_per_rhs": inst / warp_rhs if inst and warp_rhs else None,
+        "gpu_time_ms": metric(vals, "gpu__time_duration.sum"),
+    }
+    if len(args) >= 7:
+        rows = list(csv.reader(open(args[4])))
+        get = lambda name: next(float(r[-1].replace(",", "")) for r in rows if len(r) > 3 and r[-3] == name)
+        e.update(traffic_rays=int(args[5]), rk4_steps=int(args[6]), dram_bytes_read=get("dram__bytes_read.sum"),
+                 dram_bytes_write=get("dram__bytes_write.sum"), traffic_capture=os.path.basename(args[4]))
+    db[workload] = e
+    json.dump(db, open(path, "w"), indent=1, sort_keys=True)
+    print("hw counters of", workload, "->", path)
+
+
 def main():
     rep = sys.argv[1]
+    hw = None
+    if "--hw" in sys.argv:
+        i = sys.argv.index("--hw")
+        hw = sys.argv[i + 1:]
+        del sys.argv[i:]
     prefix = sys.argv[2] if len(sys.argv) > 2 else rep.rsplit(".", 1)[0]
     vals, kernel = raw(rep)
+    if hw:
+        record_hw(vals, kernel, rep, hw)
     with open(prefix + "_ncu_summary.txt", "w") as f:
         f.write(f"# ncu -i {rep.split('/')[-1]} --page raw --csv   (kernel: {kernel})\n")
         stalls = sorted(n for n in vals if "issue_stalled" in n and n.endswith("per_issue_active.ratio") and "not_issued" not in n)

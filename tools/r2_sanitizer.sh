@@ -1,0 +1,22 @@
+# compute-sanitizer memcheck over the fast / strict / depth-floor-map / same-grid / environment kernels on a subset
+# of the parity suites (small cases: the tool slows kernels ~50x)
+#   gpurun --timeout 900 -- 'bash tools/r2_sanitizer.sh r2s'
+set -x
+R=${1:-r2s}
+O=gpurun_out/$R
+mkdir -p $O
+SAN="compute-sanitizer --tool memcheck --error-exitcode 9 --print-limit 20"
+run() { # name, pytest args...
+  n=$1; shift
+  timeout 600 $SAN python -m pytest "$@" -q -x -p no:cacheprovider > $O/san_$n.log 2>&1
+  echo "exit $? : $n" >> $O/sanitizer.log
+  grep -E "ERROR SUMMARY|passed|failed" $O/san_$n.log >> $O/sanitizer.log
+}
+: > $O/sanitizer.log
+run fuzz tests/test_gpu_fuzz.py -k "0] or 1] or 2] or 3] or 4] or 5]"
+run deepmap tests/test_gpu_deep_map.py -k "dry or default or C4"
+run samegrid tests/test_gpu_same_grid.py -k "64-48 or look_alike or C5"
+run env tests/test_gpu_env.py -k "not full"
+run parity tests/test_gpu_parity.py -k "special or infinite or empty or analytic"
+run api tests/test_gpu_api.py -k "grid_lines or non_affine or negative or pitch or multiple"
+cat $O/sanitizer.log

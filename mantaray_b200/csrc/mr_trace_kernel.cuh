@@ -57,12 +57,14 @@ static constexpr int kBlock = kBlockThreads;
 #define MR_MIN_BLOCKS 7
 #endif
 // the ray state of the current step in shared memory instead of registers (fast path)
-// experiment knob: the redundant all-NaN test of k0 (see solout below); it changes ptxas's register allocation
+// experiment knob: the redundant all-NaN test of k0 (see solout below).  Without it ptxas (12.9) spills the
+// pre-step state around the stage loop unless that state is parked in shared memory (MR_FIN_SHADOW): measured
+// on C4, 51.0 ms with the test, 49.7 ms without it and with the shadow.
 #ifndef MR_K0_TEST
-#define MR_K0_TEST 1
+#define MR_K0_TEST 0
 #endif
 #ifndef MR_FIN_SHADOW
-#define MR_FIN_SHADOW 0
+#define MR_FIN_SHADOW 1
 #endif
 #ifndef MR_ROW_POINTER
 #define MR_ROW_POINTER 1

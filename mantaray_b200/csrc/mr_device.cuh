@@ -518,7 +518,7 @@ __device__ __forceinline__ double inv_root4(double x)
     return fma(t * e, p, t);
 }
 
-// E = exp(z) and em = expm1(z) for z in [-44, 0] (larger kh takes the deep-water branch).
+// E = exp(z) and em = expm1(z) for z in [-700, 0] (the callers keep z there).
 // z = n ln2 + r, |r| <= ln2/2;  expm1(r) = r + r^2 P(r) (Taylor through r^13, remainder
 // < 2e-17 relative);  E = 2^n (1 + p),  em = 2^n p + (2^n - 1)  (2^n - 1 is exact).
 __device__ __forceinline__ void exp_expm1_neg(double z, double &E, double &em)
@@ -543,7 +543,7 @@ __device__ __forceinline__ void exp_expm1_neg(double z, double &E, double &em)
     for (int i = 1; i < 12; ++i) p = fma(p, r, kExpm1C[i]);
     p = fma(r * r, p, r);                          // expm1(r)
 #endif
-    double s = __hiloint2double((n + 1023) << 20, 0);   // 2^n, n in [-64, 0]
+    double s = __hiloint2double((n + 1023) << 20, 0);   // 2^n, n in [-1010, 0]
     E = fma(s, p, s);
     em = fma(s, p, s - 1.0);
 }
@@ -558,33 +558,55 @@ __device__ __forceinline__ void exp_expm1_neg(double z, double &E, double &em)
 // propagation, so there is no per-output select.  Large kh: E -> 0, tanh = 1, second cg term
 // 0, bathymetric term -0 (the reference gets the same from cosh^2 -> inf and sinh -> inf).
 // cg and the factor (bx, by) = Bc grad(h) of dk/dt, from (k, h, grad h).
+//
+// The general expressions.  UNDER: kh may be anything >= 22, so exp(-2kh) may underflow — it is then taken as
+// exactly 0 (E = 0, expm1 = -1), which makes tanh = 1, the second cg term kh * 0 (NaN for an infinite kh, like the
+// reference's inf/inf) and the bathymetric factor -0 (NaN for an infinite k), the reference's own limits.
+template <bool UNDER>
+__device__ __forceinline__ void wave_terms_general(double k, double kh, double dhdx, double dhdy,
+                                                   double &cg, double &bx, double &by)
+{
+    // tanh kh = T, kh/cosh^2 kh = hs2, 1/(sinh kh cosh kh) = csch_sech
+    double z = -2.0 * kh, E, em;
+    const bool under = UNDER && z < -700.0;
+    if (UNDER) z = under ? -700.0 : z;             // (a NaN stays a NaN)
+    exp_expm1_neg(z, E, em);
+    if (UNDER) { E = under ? 0.0 : E; em = under ? -1.0 : em; }
+    const double m = -em, w = 2.0 + em;
+    const double r = recip(m * w);
+    const double invw = m * r;
+    const double T = m * invw;
+    const double E4 = 4.0 * E;
+    const double hs2 = kh * ((E4 * invw) * invw);
+    const double csch_sech = E4 * r;
+    const double q = (k * kExpRed[5]) * T;
+    double sq, rq;
+    sqrt_rsqrt<(MR_LEAN_SQRT & 1) != 0>(q, sq, rq);
+    cg = kExpRed[6] * ((T + hs2) * rq);
+    const double Bc = ((-0.5 * k) * csch_sech) * sq;
+    bx = Bc * dhdx; by = Bc * dhdy;
+}
+
+// Above this wavenumber the deep-water shortcut is not taken: what it drops from dk/dt, relative to k and per
+// second, is 2 exp(-2kh) sqrt(G k) |grad h| — below 2e-18 |grad h| for kh >= 22 and k <= 16 rad/m (waves longer than
+// 0.4 m, everything the model is about), but not for the k -> 1e15 of a ray creeping up to a shoreline node a few
+// femtometres deep (C5 has them): there sqrt(G k) ~ 1e8 per second and the dropped term is 1e-13 per step.
+static constexpr double kDeepMaxK = 16.0;
+
 __device__ __forceinline__ void wave_terms(double k, double h, double dhdx, double dhdy,
                                            double &cg, double &bx, double &by)
 {
     const double kh = k * h;
-    // tanh kh = T, kh/cosh^2 kh = hs2, 1/(sinh kh cosh kh) = csch_sech
     if (!(kh >= kExpRed[4])) {
-        double E, em;
-        exp_expm1_neg(-2.0 * kh, E, em);
-        const double m = -em, w = 2.0 + em;
-        const double r = recip(m * w);
-        const double invw = m * r;
-        const double T = m * invw;
-        const double E4 = 4.0 * E;
-        const double hs2 = kh * ((E4 * invw) * invw);
-        const double csch_sech = E4 * r;
-        const double q = (k * kExpRed[5]) * T;
-        double sq, rq;
-        sqrt_rsqrt<(MR_LEAN_SQRT & 1) != 0>(q, sq, rq);
-        cg = kExpRed[6] * ((T + hs2) * rq);
-        const double Bc = ((-0.5 * k) * csch_sech) * sq;
-        bx = Bc * dhdx; by = Bc * dhdy;
+        wave_terms_general<false>(k, kh, dhdx, dhdy, cg, bx, by);
+    } else if (k > kDeepMaxK) {
+        wave_terms_general<true>(k, kh, dhdx, dhdy, cg, bx, by);
     } else {
-        // Deep water, kh >= 22: exp(-2kh) < 8e-20, so in f64 tanh kh == 1 exactly, kh/cosh^2 kh < 2^-57
-        // vanishes against it, and the bathymetric term changes k by less than 3e-18 of itself per step —
-        // below half an ulp, i.e. the reference's own sum rounds it away.  With T = 1 and the other two 0 the
-        // general expressions reduce, value for value, to cg = (G/2) rsqrt(G k) and Bc = -0.  The zeros are
-        // computed, not written: kh * 0 is NaN when h (or k) is +inf, where the reference's kh/sinh(2kh) is
+        // Deep water, kh >= 22 (and k <= 16): exp(-2kh) < 8e-20, so in f64 tanh kh == 1 exactly, kh/cosh^2 kh < 2^-57
+        // vanishes against it, and the bathymetric term changes k by less than 2e-18 |grad h| of itself per second —
+        // below half an ulp per step, i.e. the reference's own sum rounds it away.  With T = 1 and the other two 0
+        // the general expressions reduce, value for value, to cg = (G/2) rsqrt(G k) and Bc = -0.  The zeros are
+        // computed, not written: kh * 0 is NaN when h is +inf, where the reference's kh/sinh(2kh) is
         // inf/inf and cg NaN, while its bathymetric term stays -0 * grad(h) for an infinite h (k * 0 is 0 then)
         // and propagates a non-finite gradient.
         const double z = kh * 0.0, zk = k * 0.0;
@@ -738,7 +760,7 @@ struct FastRay {
             if (kDmap) {
                 // (a NaN or infinite k^2 fails or passes harmlessly: NaN compares false; k^2 = inf makes k NaN,
                 // and the deep-water branch turns that into four NaNs like the general one)
-                if (!(MR_DEEP_ROOT4 && MR_DMAP_LATE_LOAD)) deep = ok && __fmul_rn((float)k2, hsq) >= 484.01f;
+                if (!(MR_DEEP_ROOT4 && MR_DMAP_LATE_LOAD)) deep = ok && __fmul_rn((float)k2, hsq) >= 484.01f && (float)k2 <= (float)(kDeepMaxK * kDeepMaxK);
                 if (!MR_DMAP_LATE_LOAD) ldg_f4_d2_unless(deep, brec, Z, gh);
             } else {
                 ldg_f4_d2(brec, Z, gh);
@@ -769,7 +791,10 @@ struct FastRay {
             k = inv_root4(k2);             // t, until phase 4
             // the map's answer is consumed only now, behind the fourth root's chain (a warp issues in order: the
             // first instruction that needs the loaded value is where it waits)
-            if (MR_DMAP_LATE_LOAD) deep = ok && __fmul_rn((float)k2, hsq) >= 484.01f;
+            if (MR_DMAP_LATE_LOAD) {
+                const float k2f = (float)k2;           // (k <= kDeepMaxK as well: see wave_terms)
+                deep = ok && __fmul_rn(k2f, hsq) >= 484.01f && k2f <= (float)(kDeepMaxK * kDeepMaxK);
+            }
             return;
         }
         double rk;

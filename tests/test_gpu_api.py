@@ -217,7 +217,9 @@ def test_multi_device_queue_balances_a_lopsided_batch(oracle, gpu):
                             trajectories=False)
     np.testing.assert_array_equal(r.rows[sel], ref.rows)
     np.testing.assert_array_equal(r.len[sel], ref.len)
-    np.testing.assert_allclose(r.final_state[:, sel], ref.final_state, rtol=1e-9, atol=0, equal_nan=True)
+    # (absolute tolerances from the rays' scales: ky is ~1e-22 where it should be 0)
+    np.testing.assert_allclose(r.final_state[:2, sel], ref.final_state[:2], rtol=0, atol=1e-9 * 1e4, equal_nan=True)
+    np.testing.assert_allclose(r.final_state[2:, sel], ref.final_state[2:], rtol=0, atol=1e-9 * 0.04, equal_nan=True)
 
 
 def test_gather_beyond_the_2d_copy_pitch_limit_goes_row_by_row(gpu, monkeypatch):

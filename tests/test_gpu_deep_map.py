@@ -143,3 +143,36 @@ def test_default_follows_the_deep_share_of_the_grid(gpu):
         assert_same(auto, mapped if deep else plain, "default flags", exact=True)
         assert_same(off, plain, "both flags", exact=True)
         assert_same(mapped, plain, "forced")
+
+
+def test_steep_cells_at_large_indices(oracle, gpu):
+    """The map's bound must hold where the lookup EXTRAPOLATES: the cell is floor() of an f32 index whose rounding
+    error grows with the index, so near column 4000 a point up to ~2e-4 cells outside a cell is still assigned to it
+    and the bilinear reaches beyond the corner values by that much of the corner difference.  Steep steps (hundreds
+    of metres per cell) straddling kh = 22 at large indices, rays sitting a few f32 ulps either side of the grid
+    lines: with the map and without it the rows, len and NaN patterns must be identical and the values agree to
+    ulps (a lane wrongly taken for deep would differ at 1e-10 or more: exp(-44) against 0 in tanh)."""
+    nx, ny, d = 4096, 12, 25.0
+    x = (np.arange(nx) * d).astype(np.float32)
+    y = (np.arange(ny) * d).astype(np.float32)
+    rng = np.random.default_rng(11)
+    k0 = 0.0402                                           # 10 s wave: kh = 22 at h = 547 m
+    # columns alternate between just shallower and much deeper than 547 m, with jitter: every 8x8 block mixes them
+    col = np.where(np.arange(nx) % 3 == 0, 540.0, 900.0) + rng.uniform(-6.0, 6.0, nx)
+    depth = np.tile(col, (ny, 1)) + rng.uniform(-3.0, 3.0, (ny, nx))
+    bathy = CartesianNetcdf3(x, y, depth)
+    cur = CartesianCurrent(x.astype(np.float64), y.astype(np.float64), 0.05 * np.ones((ny, nx)), np.zeros((ny, nx)))
+    m = 6000
+    i = rng.integers(3000, nx - 2, m)
+    ulps = rng.integers(-4, 5, m) * 2.0 ** -24
+    x0 = x[i].astype(np.float64) * (1.0 + ulps) + np.where(rng.random(m) < 0.5, 0.0, rng.uniform(0, d, m))
+    y0 = rng.uniform(2 * d, (ny - 3) * d, m)
+    kk = k0 * rng.uniform(0.97, 1.03, m)                  # kh between 21 and 37 over these depths
+    th = rng.uniform(-0.3, 0.3, m)
+    rays = (x0, y0, kk * np.cos(th), kk * np.sin(th))
+    dt, steps = 0.25, 40
+    ref = oracle.trace_many(bathy, cur, *rays, 0.0, dt * steps, dt)
+    with Fields(bathy, cur, devices=[0]) as f:
+        plain, mapped = both(f, rays, dt * steps, dt)
+    assert_parity(mapped, ref, what="steep cells at large indices, with the map")
+    assert_same(mapped, plain, "steep cells at large indices")

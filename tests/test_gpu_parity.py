@@ -13,6 +13,7 @@ from conftest import assert_parity
 from mantaray_b200 import (MR_MATH_FAST, MR_MATH_STRICT, ArrayDepth, CartesianCurrent, CartesianNetcdf3,
                            ConstantCurrent, ConstantDepth, ConstantSlope, Fields, trace_many)
 from mantaray_b200 import workloads as W
+from mantaray_b200._abi import MR_OPT_DEEP_MAP, MR_OPT_SAME_GRID
 
 pytestmark = pytest.mark.gpu
 
@@ -235,3 +236,25 @@ def test_permutation_and_restart_properties_full_size(gpu):
         assert both.sum() > 0.9 * n
         np.testing.assert_array_equal(h2.final_state[:, both], a.final_state[:, both])
         np.testing.assert_array_equal((h1.rows + h2.rows - 1)[alive], a.rows[alive])
+
+
+@pytest.mark.parametrize("math", [MR_MATH_FAST, MR_MATH_STRICT])
+def test_rays_creeping_up_to_the_shoreline(oracle, gpu, math):
+    """C5's beach: some long-period rays neither run ashore nor leave — they creep up to a shoreline node a few
+    femtometres deep while k grows without bound (1e15 ... 1e23 rad/m after 4096 steps), with kh >= 22 all the way.
+    The deep-water shortcut of the fast path must not be taken there: what it drops from dk/dt is
+    2 exp(-2kh) sqrt(G k) |grad h| relative to k, and sqrt(G k) is 1e8 per second at such k (this case was off by
+    1.3e-9 in kx before the shortcut was limited to k <= 16 rad/m)."""
+    wl = W.c5_nazare(4, 4, 64, 4096, nx=512)
+    rays = wl.all_rays()
+    ref = oracle.trace_many(wl.bathymetry, wl.current, *rays, 0.0, wl.duration, wl.dt, stride=wl.stride)
+    kfin = np.hypot(ref.final_state[2], ref.final_state[3])
+    assert np.nanmax(kfin) > 1e15 and (ref.rows[kfin > 1e6] == wl.n_steps + 1).all()      # the creepers are still alive
+    with Fields(wl.bathymetry, wl.current) as f:
+        for flags in ((0, MR_OPT_DEEP_MAP, MR_OPT_SAME_GRID) if math == MR_MATH_FAST else (0,)):
+            res = trace_many(f, *rays, 0.0, wl.duration, wl.dt, stride=wl.stride, math=math, final_state=True, flags=flags)
+            assert_parity(res, ref, what=f"shoreline creepers math={math} flags={flags}")
+            creep = kfin > 1e3
+            with np.errstate(invalid="ignore"):
+                err = np.abs(res.final_state[2:, creep] - ref.final_state[2:, creep]) / kfin[creep]
+            assert np.nanmax(err) <= 1e-12, f"k of the creeping rays off by {np.nanmax(err):.2e} (math={math}, flags={flags})"

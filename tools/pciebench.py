@@ -71,20 +71,24 @@ for k in sorted({2, 4, G} & set(range(2, G + 1))):
     timed(f"contiguous, {k} devices at once, separate pinned buffers", copy_sep(range(k)), k * n * 8, active=k, devices=k)
 del host_sep
 
-# ---- one pinned plane, each device its column block (the gather of mr_trace_many) ---------------------------
+# ---- one pinned plane, each device its column block (the gather of mr_trace_many: cudaMemcpy2DAsync) ----------
+from cuda.bindings import runtime as cudart
+
 plane = torch.empty((rows, G * w), dtype=torch.float64).pin_memory()
-dev2 = [b[: rows * w].view(rows, w) for b in dev_buf]
+D2H = cudart.cudaMemcpyKind.cudaMemcpyDeviceToHost
 
 
 def copy_cols(devs):
     def run():
         for g in devs:
-            with torch.cuda.stream(streams[g]):
-                plane[:, g * w:(g + 1) * w].copy_(dev2[g], non_blocking=True)
+            torch.cuda.set_device(g)
+            (err,) = cudart.cudaMemcpy2DAsync(plane.data_ptr() + g * w * 8, G * w * 8, dev_buf[g].data_ptr(), w * 8, w * 8, rows,
+                                              D2H, streams[g].cuda_stream)
+            assert err == cudart.cudaError_t.cudaSuccess, err
     return run
 
 
-timed("2-D column block, device 0 alone", copy_cols([0]), rows * w * 8, active=1, devices=1, row_bytes=w * 8)
+timed("2-D column block (cudaMemcpy2DAsync), device 0 alone", copy_cols([0]), rows * w * 8, active=1, devices=1, row_bytes=w * 8)
 for k in sorted({2, 4, G} & set(range(2, G + 1))):
     timed(f"2-D column blocks of one pinned plane, {k} devices at once", copy_cols(range(k)), k * rows * w * 8, active=k,
           devices=k, row_bytes=w * 8)

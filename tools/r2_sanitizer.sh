@@ -13,10 +13,11 @@ run() { # name, pytest args...
   grep -E "ERROR SUMMARY|passed|failed" $O/san_$n.log >> $O/sanitizer.log
 }
 : > $O/sanitizer.log
-run fuzz tests/test_gpu_fuzz.py -k "0] or 1] or 2] or 3] or 4] or 5]"
+MR_FUZZ_SEEDS=8 run fuzz tests/test_gpu_fuzz.py
+MR_FUZZ_SEEDS=6 run deepmap_fuzz tests/test_gpu_deep_map.py -k "fuzz or steep"
 run deepmap tests/test_gpu_deep_map.py -k "dry or default or C4"
 run samegrid tests/test_gpu_same_grid.py -k "64-48 or look_alike or C5"
 run env tests/test_gpu_env.py -k "not full"
-run parity tests/test_gpu_parity.py -k "special or infinite or empty or analytic"
+run parity tests/test_gpu_parity.py -k "special or infinite or empty or analytic or shoreline"
 run api tests/test_gpu_api.py -k "grid_lines or non_affine or negative or pitch or multiple"
 cat $O/sanitizer.log

@@ -550,7 +550,7 @@ def main():
 
         avail = psutil.virtual_memory().available
         per_ray = 32.0 * rows_cap if full else 0.0
-        budget = min(0.30 * avail / max(local_world, 1), 70e9)
+        budget = min(0.50 * avail / max(local_world, 1), 70e9)
         n_e2e = n if per_ray == 0 else int(min(n, max(budget // per_ray, 1024)))
         n_e2e = max(n_e2e // 128 * 128, min(n, 128))
         sel = slice(0, n_e2e)
@@ -588,7 +588,7 @@ def main():
             "d2h_bytes_per_step": int((per_ray + 8 + 32) * n_e2e_all),
             "rays_per_step": n_e2e_all, "rays_per_step_per_rank": int(n_e2e), "steps": e2e_steps, "ms_per_step": 1e3 * el / e2e_steps,
             "d2h_GB_per_s": (per_ray + 8 + 32) * n_e2e_all * e2e_steps / el / 1e9,
-            "batch_note": ("the per-rank batch is what 30 %% of the free host RAM / %d ranks holds as pinned planes "
+            "batch_note": ("the per-rank batch is what 50 %% of the free host RAM / %d ranks holds as pinned planes "
                            "(%.1f GB per rank): smaller than the %d rays per GPU of the kernel line when several ranks share the host" % (
                                local_world, per_ray * n_e2e / 1e9, n)) if n_e2e < n else "the whole per-GPU batch",
             "api": "mr_trace_many (C ABI, pinned host buffers, H2D of the ray states and D2H of every stored row inside the timed region)",

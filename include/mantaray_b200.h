@@ -141,6 +141,15 @@ typedef struct mr_trace_opts {
  * library does not choose it by itself.  Ignored where the grids differ.
  *   MR_OPT_SAME_GRID : use the shortcut where the two grids coincide                                   */
 #define MR_OPT_SAME_GRID 4
+/* Uniform-current map.  The API always takes a current file, so "no current" is a grid of zeros; step currents are
+ * piecewise constant.  Where a block of 8 x 8 cells of an affine current grid holds one u and one v, the reference's
+ * bilinear returns exactly that value and its finite differences are exactly 0, so MR_MATH_FAST reads 8 bytes of a
+ * small map there instead of the 64-byte cell record and skips the interpolation: the same values.
+ * By default the library uses the map when at least half of the grid's blocks are uniform.
+ *   MR_OPT_CURRENT_MAP    : use it whenever the grid has one
+ *   MR_OPT_NO_CURRENT_MAP : never use it (wins)                                                       */
+#define MR_OPT_CURRENT_MAP    8
+#define MR_OPT_NO_CURRENT_MAP 16
 
 /* ---- library ------------------------------------------------------------- */
 
@@ -340,6 +349,15 @@ void mr_host_free(void *p);
  * CUDA device. */
 int  mr_depth_floor_map(const mr_bathymetry_desc *bathy, float *out, size_t cap,
                         int32_t *nbx, int32_t *nby, float *deep_frac, int32_t *affine);
+
+/* The uniform-current map MR_OPT_CURRENT_MAP consults, as the library builds it for a GRID current at upload: two
+ * floats {u, v} per block of 8 x 8 cells, row-major [*nby][*nbx][2] — the value of EVERY node the block's cells touch
+ * where they all hold the same finite u and the same finite v (compared as doubles), NaNs elsewhere.  `out` may be
+ * NULL to query the shape; `cap` is its capacity in floats.  *uniform_frac (may be NULL): the share of uniform
+ * blocks.  *affine (may be NULL): 1 if the grid's coordinates, cast to f32, are exactly affine, which is when the
+ * fast path uses the map at all.  Host only: works without a CUDA device. */
+int  mr_uniform_current_map(const mr_current_desc *current, float *out, size_t cap,
+                            int32_t *nbx, int32_t *nby, float *uniform_frac, int32_t *affine);
 
 #ifdef __cplusplus
 }

@@ -8,8 +8,9 @@ runs as hand-written sm_100a CUDA kernels behind the C ABI of
 library, calling into it does (and fails loudly when it is missing).
 """
 
-from ._abi import MR_MATH_FAST, MR_MATH_STRICT, MR_OPT_DEEP_MAP, MR_OPT_NO_DEEP_MAP, MR_OPT_SAME_GRID
-from ._capi import (Fields, ManyRays, MantarayError, RayState, SingleRay, TraceResult, depth_floor_map, sample_fields,
+from ._abi import (MR_MATH_FAST, MR_MATH_STRICT, MR_OPT_CURRENT_MAP, MR_OPT_DEEP_MAP, MR_OPT_NO_CURRENT_MAP,
+                   MR_OPT_NO_DEEP_MAP, MR_OPT_SAME_GRID)
+from ._capi import (Fields, ManyRays, MantarayError, RayState, SingleRay, TraceResult, depth_floor_map, sample_fields, uniform_current_map,
                     trace_many)
 from ._mantaray import cache_info, clear_cache
 from .core import ray_tracing, single_ray
@@ -18,8 +19,8 @@ from .fields import (ArrayDepth, CartesianCurrent, CartesianNetcdf3, ConstantCur
 
 __all__ = [
     "single_ray", "ray_tracing", "clear_cache", "cache_info",
-    "ManyRays", "SingleRay", "RayState", "Fields", "TraceResult", "trace_many", "sample_fields", "depth_floor_map",
+    "ManyRays", "SingleRay", "RayState", "Fields", "TraceResult", "trace_many", "sample_fields", "depth_floor_map", "uniform_current_map",
     "MantarayError",
     "ConstantDepth", "ConstantSlope", "CartesianNetcdf3", "ArrayDepth", "ConstantCurrent", "CartesianCurrent",
-    "MR_MATH_FAST", "MR_MATH_STRICT", "MR_OPT_DEEP_MAP", "MR_OPT_NO_DEEP_MAP", "MR_OPT_SAME_GRID",
+    "MR_MATH_FAST", "MR_MATH_STRICT", "MR_OPT_DEEP_MAP", "MR_OPT_NO_DEEP_MAP", "MR_OPT_SAME_GRID", "MR_OPT_CURRENT_MAP", "MR_OPT_NO_CURRENT_MAP",
 ]

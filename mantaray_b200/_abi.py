@@ -73,6 +73,8 @@ class CurrentDesc(C.Structure):
 MR_OPT_DEEP_MAP = 1
 MR_OPT_NO_DEEP_MAP = 2
 MR_OPT_SAME_GRID = 4
+MR_OPT_CURRENT_MAP = 8
+MR_OPT_NO_CURRENT_MAP = 16
 
 
 class TraceOpts(C.Structure):
@@ -157,6 +159,8 @@ SIGNATURES = {
     "mr_fields_last_split": (C.c_int, [C.c_void_p, c_int64_p, C.c_int32]),
     "mr_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
     "mr_host_free": (None, [C.c_void_p]),
+    "mr_uniform_current_map": (C.c_int, [C.POINTER(CurrentDesc), C.c_void_p, C.c_size_t, c_int32_p, c_int32_p,
+                                         C.POINTER(C.c_float), c_int32_p]),
     "mr_depth_floor_map": (C.c_int, [C.POINTER(BathymetryDesc), C.c_void_p, C.c_size_t, c_int32_p, c_int32_p,
                                      C.POINTER(C.c_float), c_int32_p]),
 }

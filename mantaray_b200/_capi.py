@@ -399,3 +399,16 @@ def depth_floor_map(bathy):
     _check(lib.mr_depth_floor_map(C.byref(bd), out.ctypes.data, out.size, C.byref(nbx), C.byref(nby), C.byref(frac),
                                   C.byref(aff)))
     return out, frac.value, bool(aff.value)
+
+
+def uniform_current_map(current):
+    """``mr_uniform_current_map``: ``(map[nby, nbx, 2] f32, uniform_frac, affine)`` — per block of 8 x 8 cells the
+    {u, v} every node of the block holds, NaNs where the block is not uniform.  Host only."""
+    lib = load()
+    cd = current.to_desc()
+    nbx, nby, frac, aff = C.c_int32(), C.c_int32(), C.c_float(), C.c_int32()
+    _check(lib.mr_uniform_current_map(C.byref(cd), None, 0, C.byref(nbx), C.byref(nby), C.byref(frac), C.byref(aff)))
+    out = np.empty((nby.value, nbx.value, 2), dtype=np.float32)
+    _check(lib.mr_uniform_current_map(C.byref(cd), out.ctypes.data, out.size, C.byref(nbx), C.byref(nby), C.byref(frac),
+                                      C.byref(aff)))
+    return out, frac.value, bool(aff.value)

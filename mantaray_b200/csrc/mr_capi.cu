@@ -86,6 +86,7 @@ struct DeviceFields {
     BathyDev b{};
     CurrentDev c{};
     float deep_frac = 0.0f;    // share of the depth-floor map's blocks that are deep water for a 10 s wave
+    float cuni_frac = 0.0f;    // share of the uniform-current map's blocks that are uniform
     size_t max_pitch = 0;      // cudaDevAttrMaxPitch: the largest pitch cudaMemcpy2D accepts
     int64_t last_taken = 0;    // rays this device took from the slab queue in the last host-buffer call
     std::vector<void *> allocs;
@@ -270,6 +271,35 @@ static std::vector<float> depth_floor_map(const double *depth, int nx, int ny, i
     return out;
 }
 
+// Uniform-current map of the fast path (FastRay, CMAP): for every block of kDeepBlock x kDeepBlock cells, {u, v} as
+// f32 (`as f32`, cartesian_current.rs:378) if all nodes the block's cells touch hold one finite u and one finite v
+// (compared as f64: only then are the f64 finite differences of cartesian_current.rs:522-536 exactly 0), else NaNs.
+static std::vector<float> uniform_current_map(const double *u, const double *v, int nx, int ny, int *nbx_out, float *frac)
+{
+    const int B = kDeepBlock;
+    const int nbx = (nx - 1 + B - 1) / B, nby = (ny - 1 + B - 1) / B;
+    std::vector<float> out((size_t)nbx * (size_t)nby * 2, NAN);
+    size_t n_uni = 0;
+    for (int by = 0; by < nby; ++by) {
+        const int j0 = by * B, j1 = std::min(j0 + B, ny - 1);
+        for (int bx = 0; bx < nbx; ++bx) {
+            const int i0 = bx * B, i1 = std::min(i0 + B, nx - 1);
+            const double u0 = u[(size_t)j0 * (size_t)nx + (size_t)i0], v0 = v[(size_t)j0 * (size_t)nx + (size_t)i0];
+            bool same = std::isfinite(u0) && std::isfinite(v0);
+            for (int j = j0; j <= j1 && same; ++j)
+                for (int i = i0; i <= i1; ++i)
+                    if (u[(size_t)j * (size_t)nx + (size_t)i] != u0 || v[(size_t)j * (size_t)nx + (size_t)i] != v0) { same = false; break; }
+            if (!same) continue;
+            out[2 * ((size_t)by * (size_t)nbx + (size_t)bx)] = (float)u0;
+            out[2 * ((size_t)by * (size_t)nbx + (size_t)bx) + 1] = (float)v0;
+            ++n_uni;
+        }
+    }
+    *nbx_out = nbx;
+    *frac = (float)n_uni / (float)std::max<size_t>((size_t)nbx * (size_t)nby, 1);
+    return out;
+}
+
 // change-of-basis coefficients of interpolator.rs:64-72 for a (dx, dy) cell, in f32
 static bool basis_coeffs(float dx, float dy, float *c01, float *c10)
 {
@@ -381,6 +411,15 @@ static int upload_fields(DeviceFields &d, const mr_bathymetry_desc *b, const mr_
             return (unsigned long long)a | ((unsigned long long)b2 << 32);
         };
         C.p0 = pack2c(C.xf0, C.yf0); C.d2 = pack2c(C.dxf, C.dyf); C.c2 = pack2c(C.c10, C.c01);
+        C.cmap = nullptr; C.cmap_nbx = 0;
+        if (C.uniform) {
+            int nbx = 0;
+            std::vector<float> cm = uniform_current_map(c->u, c->v, c->nx, c->ny, &nbx, &d.cuni_frac);
+            const float *dev = nullptr;
+            if ((rc = upload(d, cm.data(), cm.size(), &dev))) return rc;
+            C.cmap = reinterpret_cast<const float2 *>(dev);
+            C.cmap_nbx = nbx;
+        }
     }
     // Same-grid shortcut (FastRay, SG): the current lives on the bathymetry's grid — same shape, bit-identical f32
     // coordinates and basis, f64 coordinates that are exactly the f32 ones widened — so one f32 fractional index
@@ -460,6 +499,16 @@ static int want_deep_map(const DeviceFields &d, const mr_trace_opts &o)
     return (o.flags & MR_OPT_DEEP_MAP) != 0 || d.deep_frac >= kDeepMapAutoShare;
 }
 
+// The uniform-current map: used when at least half of the current grid's blocks are uniform (a zero-current file,
+// a piecewise-constant current) — elsewhere it only puts a dependent load in front of every record load.
+// MR_OPT_CURRENT_MAP forces it on for any grid that has one, MR_OPT_NO_CURRENT_MAP off.
+static constexpr float kCurrentMapAutoShare = 0.5f;
+static int want_current_map(const DeviceFields &d, const mr_trace_opts &o)
+{
+    if (o.flags & MR_OPT_NO_CURRENT_MAP) return 0;
+    return (o.flags & MR_OPT_CURRENT_MAP) != 0 || d.cuni_frac >= kCurrentMapAutoShare;
+}
+
 static int enqueue_trace(const DeviceFields &d, cudaStream_t stream, int64_t n,
                          const double *x0, const double *y0, const double *kx0, const double *ky0,
                          double dt, int64_t nsteps, const mr_trace_opts &o,
@@ -474,6 +523,7 @@ static int enqueue_trace(const DeviceFields &d, cudaStream_t stream, int64_t n,
     a.rows = rows; a.len = len; a.fin = fin;
     a.deep_map = want_deep_map(d, o);
     a.same_grid = (o.flags & MR_OPT_SAME_GRID) != 0;
+    a.current_map = want_current_map(d, o);
     cudaError_t e;
     if (o.math == MR_MATH_STRICT) e = launch_trace_strict(a, stream);
     else if (o.math == MR_MATH_FAST) e = launch_trace_fast(a, stream);
@@ -682,6 +732,7 @@ static int trace_slabs_on_device(DeviceFields &d, const HostJob &j, SlabQueue &q
                 a.rows = B.rows; a.len = B.len; a.fin = B.fin;
                 a.deep_map = want_deep_map(d, j.o);
                 a.same_grid = (j.o.flags & MR_OPT_SAME_GRID) != 0;
+                a.current_map = want_current_map(d, j.o);
                 // fin is [4][n] with n = m for the kernel (it uses a.n as the pitch)
                 cudaError_t e = j.o.math == MR_MATH_STRICT ? launch_trace_strict(a, s_comp) : launch_trace_fast(a, s_comp);
                 if (e != cudaSuccess) { rc = bail(MR_ERR_CUDA, std::string("trace kernel launch: ") + cudaGetErrorString(e)); goto done; }
@@ -1133,6 +1184,33 @@ int mr_depth_floor_map(const mr_bathymetry_desc *b, float *out, size_t cap, int3
     }
     return MR_OK;
     MR_API_END("mr_depth_floor_map")
+}
+
+int mr_uniform_current_map(const mr_current_desc *c, float *out, size_t cap, int32_t *nbx, int32_t *nby,
+                           float *uniform_frac, int32_t *affine)
+{
+    MR_API_BEGIN
+    if (!c || !nbx || !nby) return fail(MR_ERR_BAD_ARG, "mr_uniform_current_map: NULL argument");
+    if (c->kind != MR_CURRENT_GRID || c->nx < 2 || c->ny < 2 || !c->x || !c->y || !c->u || !c->v)
+        return fail(MR_ERR_BAD_ARG, "mr_uniform_current_map: needs a GRID current with nx, ny >= 2");
+    if (affine) {       // the same test upload_fields applies before it builds (and the kernel consults) the map
+        std::vector<float> xf((size_t)c->nx), yf((size_t)c->ny);
+        for (int i = 0; i < c->nx; ++i) xf[(size_t)i] = (float)c->x[i];
+        for (int i = 0; i < c->ny; ++i) yf[(size_t)i] = (float)c->y[i];
+        float dxf, dyf, c01, c10;
+        *affine = affine_f32(xf.data(), c->nx, &dxf) && affine_f32(yf.data(), c->ny, &dyf) && basis_coeffs(dxf, dyf, &c01, &c10);
+    }
+    int bx = 0;
+    float frac = 0.0f;
+    const std::vector<float> m = uniform_current_map(c->u, c->v, c->nx, c->ny, &bx, &frac);
+    *nbx = bx; *nby = bx ? (int32_t)(m.size() / 2 / (size_t)bx) : 0;
+    if (uniform_frac) *uniform_frac = frac;
+    if (out) {
+        if (cap < m.size()) return fail(MR_ERR_BAD_ARG, "mr_uniform_current_map: output too small");
+        std::memcpy(out, m.data(), m.size() * sizeof(float));
+    }
+    return MR_OK;
+    MR_API_END("mr_uniform_current_map")
 }
 
 // ---- NetCDF-3 ---------------------------------------------------------------

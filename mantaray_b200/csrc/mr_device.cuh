@@ -128,6 +128,12 @@ struct CurrentDev {
     int32_t uniform;
     float xf0, yf0, dxf, dyf, c01, c10;
     f32x2 p0, d2, c2;          // {x0,y0} {dx,dy} {c10,c01} as f32 pairs
+    // uniform-current map (see FastRay, CMAP): per block of kDeepBlock x kDeepBlock cells, {u, v} as f32 where every
+    // node the block's cells touch holds the same u and the same v (then the reference's bilinear returns exactly
+    // that value anywhere in the block and all four finite differences are exactly 0), {NaN, NaN} elsewhere;
+    // [cmap_nby][cmap_nbx] float2, row-major
+    const float2 *cmap;
+    int32_t cmap_nbx;
 };
 
 static constexpr double kG = 9.8;            // src/wave_ray_path.rs:23
@@ -649,17 +655,25 @@ __device__ __forceinline__ void wave_terms(double k, double h, double dhdx, doub
 // geometry (corner coordinates, in-cell fractions, the corner-coincidence test of interpolator.rs:46-50) is then
 // shared too.  Within sg_delta of a grid line (< 0.2 % of evaluations per axis on a 2048-point axis) the lane takes
 // the two separate lookups exactly as without SG.  Every value is the one the separate lookups produce.
-template <int BK, int CK, bool UNI, bool DMAP = false, bool SG = false>
+// CMAP (affine gridded current): zero-current files (the API always takes a current file) and piecewise-constant
+// currents are common; where a block of the current grid is uniform the lookup degenerates — the reference's
+// bilinear of four equal corners is that value, its finite differences are 0 — so a lane there loads 8 bytes of a
+// small map (shared by all lanes of the block) instead of its 64-byte cell record and skips the bilinear and the
+// corner test; the bounds test of the f64 index stays.  Lanes in other blocks load their record as without the map.
+template <int BK, int CK, bool UNI, bool DMAP = false, bool SG = false, bool CMAP = false>
 struct FastRay {
     static constexpr bool kDmap = DMAP && UNI && BK == MR_BATHY_GRID;
+    static constexpr bool kCmap = CMAP && UNI && CK == MR_CURRENT_GRID && !SG;
     static constexpr bool kSame = SG && UNI && BK == MR_BATHY_GRID && CK == MR_CURRENT_GRID;
     // advection sums formed ahead of the bilinears: in the variants that need the registers (measured: the plain
     // kernel is 8 % slower with it, 63.9 -> 69.2 ms on C4)
-    static constexpr bool kEarly = CK == MR_CURRENT_GRID && ((MR_EARLY_GRAD & 1) && !kDmap && !kSame || (MR_EARLY_GRAD & 2) && kDmap && !kSame || (MR_EARLY_GRAD & 4) && kSame);
+    static constexpr bool kEarly = !(CMAP && !SG) && CK == MR_CURRENT_GRID && ((MR_EARLY_GRAD & 1) && !kDmap && !kSame || (MR_EARLY_GRAD & 2) && kDmap && !kSame || (MR_EARLY_GRAD & 4) && kSame);
     static constexpr bool kShare = kSame && !kDmap && MR_SG_SHARE_GEOM;      // one cell geometry for both lookups (with the map the depth lookup is the rare path)
     float xf, yf;
     bool ok;
     bool deep;
+    bool cuni;                 // kCmap: this lane's block of the current grid is uniform
+    float2 cm;                 // kCmap: the block's {u, v}, or NaNs
     float hsq;
     int bx1, by1, cx1, cy1;
     const float4 *brec;
@@ -738,6 +752,9 @@ struct FastRay {
                 ok = ok && okc;
             }
             ccell = (unsigned)((c.nx - 1) * cy1 + cx1);
+            if (kCmap)
+                asm volatile("ld.global.nc.v2.f32 {%0,%1}, [%2];" : "=f"(cm.x), "=f"(cm.y)
+                             : "l"(c.cmap + (unsigned)((cy1 >> kDeepShift) * c.cmap_nbx + (cx1 >> kDeepShift))));
         }
         return true;
     }
@@ -770,7 +787,10 @@ struct FastRay {
                 bya = __ldg(b.y + by1); byb = __ldg(b.y + by1 + 1);
             }
         }
-        if (CK == MR_CURRENT_GRID) {
+        if (CK == MR_CURRENT_GRID && kCmap) {
+            // the lanes outside uniform blocks fetch their record when they get to the bilinear (current_part):
+            // one more exposed round trip for them, sixteen registers fewer held by everybody
+        } else if (CK == MR_CURRENT_GRID) {
             ldg_f4_f4(c.cell + 4u * ccell, U, V);
             ldg_d2_d2((const double2 *)(c.cell + 4u * ccell + 2), gu, gv);
             if (!UNI) {
@@ -851,6 +871,19 @@ struct FastRay {
     // current and its gradients at (xf, yf); *keep (kSame) receives the cell geometry for the bathymetry to reuse
     __device__ __forceinline__ void current_part(const CurrentDev &c, f32x2 p, CurrentVal &cv, Geom *keep = nullptr)
     {
+        if (kCmap) cuni = cm.x == cm.x;             // not the NaN marker
+        if (kCmap && cuni) {
+            // four equal corners: interpolator.rs:78-83 gives a10 = a01 = a11 = 0 and returns the corner value (X and
+            // Y are finite inside the grid, and a coinciding corner returns the same value); the finite differences
+            // of cartesian_current.rs:522-536 are exactly 0
+            cv.u = (double)cm.x; cv.v = (double)cm.y;
+            cv.dudx = cv.dudy = cv.dvdx = cv.dvdy = 0.0;
+            return;
+        }
+        if (kCmap) {
+            ldg_f4_f4(c.cell + 4u * ccell, U, V);
+            ldg_d2_d2((const double2 *)(c.cell + 4u * ccell + 2), gu, gv);
+        }
         if (CK == MR_CURRENT_GRID) {
             float X, Y;
             if (UNI) {
@@ -986,7 +1019,7 @@ struct FastRay {
         // round trip, issued the other loads, and waited again (profiles/r1/g_*).  OR-ing in
         // (bits of the current record) & 0 — a zero the compiler cannot see — changes no value but
         // makes the first bathymetry consumer depend on both loads, so both are in flight first.
-        if (BK == MR_BATHY_GRID && CK == MR_CURRENT_GRID)
+        if (BK == MR_BATHY_GRID && CK == MR_CURRENT_GRID && !kCmap)
             Z.x = __int_as_float(__float_as_int(Z.x) | (__float_as_int(U.x) & b.zero));
         float h32;
         double dhdx, dhdy;
@@ -1009,7 +1042,7 @@ struct FastRay {
 };
 
 // The RHS of NR rays carried by one thread, phase by phase.
-template <int BK, int CK, bool UNI, int NR, bool DMAP, bool SG>
+template <int BK, int CK, bool UNI, int NR, bool DMAP, bool SG, bool CMAP>
 __device__ __forceinline__ void rhs_fast_n(const BathyDev &b, const CurrentDev &c,
                                            const double (&s)[NR][4], double (&out)[NR][4])
 {
@@ -1032,7 +1065,7 @@ __device__ __forceinline__ void rhs_fast_n(const BathyDev &b, const CurrentDev &
         }
         return;
     }
-    FastRay<BK, CK, UNI, DMAP, false> ray[NR];
+    FastRay<BK, CK, UNI, DMAP, false, CMAP> ray[NR];
 #pragma unroll
     for (int r = 0; r < NR; ++r) ray[r].phase1(b, c, s[r][0], s[r][1], s[r][2], s[r][3]);
 #pragma unroll
@@ -1046,7 +1079,7 @@ __device__ __forceinline__ void rhs_fast_n(const BathyDev &b, const CurrentDev &
 // =============================================================================
 // System::system (wave_ray_path.rs:220-234): Err -> four NaN
 // =============================================================================
-template <int BK, int CK, int MATH, bool UNI, int NR, bool DMAP = false, bool SG = false>
+template <int BK, int CK, int MATH, bool UNI, int NR, bool DMAP = false, bool SG = false, bool CMAP = false>
 __device__ __forceinline__ void rhs(const BathyDev &b, const CurrentDev &c,
                                     const double (&s)[NR][4], double (&out)[NR][4])
 {
@@ -1067,7 +1100,7 @@ __device__ __forceinline__ void rhs(const BathyDev &b, const CurrentDev &c,
             else rhs_f64_strict(kx, ky, (double)h32, (double)gx32, (double)gy32, cv, out[r]);
         }
     } else {
-        rhs_fast_n<BK, CK, UNI, NR, DMAP, SG>(b, c, s, out);
+        rhs_fast_n<BK, CK, UNI, NR, DMAP, SG, CMAP>(b, c, s, out);
     }
 }
 

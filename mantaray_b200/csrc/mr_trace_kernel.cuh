@@ -41,6 +41,7 @@ struct TraceArgs {
     double *fin;               // [4][n] or NULL
     int32_t deep_map;          // use the bathymetry's depth-floor map where the grids allow it (MR_OPT_DEEP_MAP)
     int32_t same_grid;         // use the same-grid shortcut where the grids allow it (MR_OPT_SAME_GRID)
+    int32_t current_map;       // use the uniform-current map where the current grid has one
     // filled by launch_trace_math: the trajectory planes as byte offsets from the x plane, the row pitch in bytes
     int64_t off_y, off_kx, off_ky, row_bytes;
     double sixth;              // dt / 6 (read from here by the depth-floor-map variant, which is short of registers)
@@ -125,7 +126,7 @@ __device__ __forceinline__ void store_count(const TraceArgs &a, int32_t *dst, in
 // Per-ray bookkeeping is event-driven: `rows` is written when the ray stops and `len` when its first NaN
 // appears (each at most once per ray, re-deriving the ray index on the spot), so the step loop carries two
 // flags and one row pointer per thread; the step number and the store countdown are warp-uniform.
-template <int BK, int CK, int MATH, bool UNI, bool DMAP, bool SG>
+template <int BK, int CK, int MATH, bool UNI, bool DMAP, bool SG, bool CMAP>
 __global__ void __launch_bounds__(kBlock, (MATH == MR_MATH_FAST) ? (UNI ? (DMAP ? MR_MIN_BLOCKS_DMAP : MR_MIN_BLOCKS) : MR_MIN_BLOCKS_GENERIC) : 1)
 trace_kernel(const __grid_constant__ TraceArgs a)
 {
@@ -201,7 +202,7 @@ trace_kernel(const __grid_constant__ TraceArgs a)
                     // +0, which the strict path must not allow)
                     yt[0][c] = (MATH == MR_MATH_STRICT && st == 0) ? yc : adv;
                 }
-                rhs<BK, CK, MATH, UNI, 1, DMAP, SG>(a.b, a.c, yt, k);
+                rhs<BK, CK, MATH, UNI, 1, DMAP, SG, CMAP>(a.b, a.c, yt, k);
 #if MR_K0_TEST
                 if (st == 0) k0_nan = all_nan4(k[0]);
 #endif
@@ -312,14 +313,19 @@ static cudaError_t launch_trace_math(const TraceArgs &args, cudaStream_t stream)
     const bool dmap = uni && a.deep_map && a.b.kind == MR_BATHY_GRID && a.b.dmap != nullptr;
     // the same-grid shortcut needs both fields gridded, affine, and on one grid (BathyDev::same_grid, set at upload)
     const bool sg = uni && a.same_grid && a.b.kind == MR_BATHY_GRID && a.c.kind == MR_CURRENT_GRID && a.b.same_grid;
+    // the uniform-current map needs the affine fast path on a gridded current that has one (not with the shortcut)
+    const bool cmap = uni && !sg && a.current_map && a.c.kind == MR_CURRENT_GRID && a.c.cmap != nullptr;
 #define MR_LAUNCH(BKV, CKV, UNIV)                                                                              \
     do {                                                                                                       \
         constexpr bool kGG = kFast && UNIV && BKV == MR_BATHY_GRID && CKV == MR_CURRENT_GRID;                  \
         constexpr bool kBG = kFast && UNIV && BKV == MR_BATHY_GRID;                                            \
-        if (dmap && sg) trace_kernel<BKV, CKV, MATH, UNIV, kBG, kGG><<<grid, kBlock, 0, stream>>>(a);          \
-        else if (dmap) trace_kernel<BKV, CKV, MATH, UNIV, kBG, false><<<grid, kBlock, 0, stream>>>(a);         \
-        else if (sg) trace_kernel<BKV, CKV, MATH, UNIV, false, kGG><<<grid, kBlock, 0, stream>>>(a);           \
-        else trace_kernel<BKV, CKV, MATH, UNIV, false, false><<<grid, kBlock, 0, stream>>>(a);                 \
+        constexpr bool kCG = kFast && UNIV && CKV == MR_CURRENT_GRID;                                          \
+        if (dmap && sg) trace_kernel<BKV, CKV, MATH, UNIV, kBG, kGG, false><<<grid, kBlock, 0, stream>>>(a);   \
+        else if (sg) trace_kernel<BKV, CKV, MATH, UNIV, false, kGG, false><<<grid, kBlock, 0, stream>>>(a);    \
+        else if (dmap && cmap) trace_kernel<BKV, CKV, MATH, UNIV, kBG, false, kCG><<<grid, kBlock, 0, stream>>>(a); \
+        else if (cmap) trace_kernel<BKV, CKV, MATH, UNIV, false, false, kCG><<<grid, kBlock, 0, stream>>>(a);  \
+        else if (dmap) trace_kernel<BKV, CKV, MATH, UNIV, kBG, false, false><<<grid, kBlock, 0, stream>>>(a);  \
+        else trace_kernel<BKV, CKV, MATH, UNIV, false, false, false><<<grid, kBlock, 0, stream>>>(a);          \
     } while (0)
 #define MR_CASE(BKV, CKV)                                                                                      \
     if (a.b.kind == BKV && a.c.kind == CKV) {                                                                  \

@@ -257,3 +257,42 @@ def test_field_handle_cache_keys_on_the_files_and_evicts(tmp_path, monkeypatch):
     with _mantaray._open_fields(str(b2), str(c), [0]) as f5:
         pass
     assert freed[-1] == f5.key and _mantaray.cache_info()["entries"] == 0
+
+
+def test_uniform_current_map_is_sound_against_the_oracle_lookup():
+    """mr_uniform_current_map (host only): in every block it marks uniform, the reference's lookup
+    (cartesian_current.rs:487-542, here the oracle's) returns exactly the block's {u, v} and exactly zero gradients
+    at any point the lookup assigns to one of the block's cells; blocks with a node off by one ulp, a NaN or an
+    infinity are not marked."""
+    from mantaray_b200 import CartesianCurrent, uniform_current_map
+    from oracle import mr_oracle as O
+
+    O.build()
+    nx, ny, d = 61, 37, 25.0
+    x, y = np.arange(nx) * d, np.arange(ny) * d
+    X, Y = np.meshgrid(np.arange(nx), np.arange(ny))
+    u = np.where(X < 24, 0.0, 0.7).astype(np.float64)
+    v = np.where(Y < 16, 0.25, -0.1).astype(np.float64)
+    u[20:30, 30:42] += 0.3 * np.sin(X[20:30, 30:42])
+    v[5, 9] = np.nextafter(0.25, 1.0)
+    u[33, 50], v[3, 55] = np.nan, np.inf
+    cur = CartesianCurrent(x, y, u, v)
+    m, frac, affine = uniform_current_map(cur)
+    assert affine and m.shape == ((ny - 1 + 7) // 8, (nx - 1 + 7) // 8, 2) and 0.3 < frac < 0.9
+    uni = ~np.isnan(m[..., 0])
+    assert not uni[0, 1] and not uni[4, 6] and not uni[0, 6]          # the ulp, the NaN, the infinity
+    assert not uni[2, 2] and not uni[2, 3]                            # u steps from 0 to 0.7 at column 24: blocks 2 and 3 touch it
+    rng = np.random.default_rng(0)
+    n_checked = 0
+    for by, bx in zip(*np.nonzero(uni)):
+        for _ in range(6):
+            px = rng.uniform(bx * 8 * d, min((bx + 1) * 8, nx - 1) * d)
+            py = rng.uniform(by * 8 * d, min((by + 1) * 8, ny - 1) * d)
+            (cu, cv), ((dudx, dudy), (dvdx, dvdy)) = O.current_and_gradient(cur, px, py)
+            assert (np.float32(cu), np.float32(cv)) == (m[by, bx, 0], m[by, bx, 1]) and dudx == dudy == dvdx == dvdy == 0.0
+            n_checked += 1
+    assert n_checked > 100
+    # a zero-current file (what "no current" looks like through the API) is uniform everywhere
+    zero = CartesianCurrent(x, y, np.zeros((ny, nx)), np.zeros((ny, nx)))
+    mz, fz, _ = uniform_current_map(zero)
+    assert fz == 1.0 and (mz == 0.0).all()

@@ -308,7 +308,7 @@ def main():
     import torch
     import torch.distributed as dist
 
-    from mantaray_b200 import CartesianNetcdf3, _abi, _capi
+    from mantaray_b200 import CartesianCurrent, CartesianNetcdf3, _abi, _capi
     from mantaray_b200 import workloads as W
     from tools import mrtools
 
@@ -402,6 +402,11 @@ def main():
         if args.math == "fast" and isinstance(wl.bathymetry, CartesianNetcdf3):
             _, deep_share, affine = _capi.depth_floor_map(wl.bathymetry)
             deep_map_used = bool(affine) and args.deep_map != "off" and (args.deep_map == "on" or deep_share >= 0.25)
+        # likewise the uniform-current map: on affine current grids whose blocks are at least half uniform
+        cur_map_used, cur_share = False, None
+        if args.math == "fast" and args.same_grid == "off" and isinstance(wl.current, CartesianCurrent):
+            _, cur_share, c_affine = _capi.uniform_current_map(wl.current)
+            cur_map_used = bool(c_affine) and cur_share >= 0.5
         launches = C.c_int32(0)
         p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
 
@@ -460,7 +465,8 @@ def main():
         alg_flop = E_local * wl.flop_per_ray_step
         ach_tf = alg_flop / (kernel_ms * 1e-3) / 1e12
         ach_gbs = alg_bytes / (kernel_ms * 1e-3) / 1e9
-        variant = [args.math] + (["depth-floor map"] if deep_map_used else [])
+        variant = [args.math] + (["depth-floor map"] if deep_map_used else []) + (["uniform-current map"] if cur_map_used else []) + \
+                  (["same-grid"] if args.same_grid == "on" else [])
         kname = "mr::trace_kernel<GRID,GRID,%s>" % ",".join(variant)
         hw, traffic = None, None
         cap = hw_counters.get(wl.name)
@@ -526,6 +532,7 @@ def main():
             "executed_ray_steps_per_pass": E, "shard": shard_mode,
             "per_rank_ms": per_rank_ms, "imbalance_max_over_mean": max(per_rank_ms) / (sum(per_rank_ms) / len(per_rank_ms)),
             "deep_map": {"flag": args.deep_map, "used": deep_map_used, "deep_share_of_blocks": deep_share},
+            "current_map": {"used": cur_map_used, "uniform_share_of_blocks": cur_share},
             "l2": ("each pass writes %.1f GB per GPU, far more than the 126 MB L2: no flush needed" % (out_bytes / 1e9)) if not need_flush
                   else "256 MB buffer written before every timed pass (outside the timed interval)",
             "roofline": roofline, "roofline_hbm": roofline_hbm, "parity": parity, "gpu_launches": int(allsum(float(n_launch))),
@@ -630,7 +637,7 @@ def main():
                 "workload": wl.name, "description": wl.description, "rays": wl.n_rays, "rays_per_gpu": n,
                 "rk4_steps": wl.n_steps, "grid": head["grid"],
                 "stride": wl.stride, "output": wl.output, "math": args.math,
-                "deep_map": head["deep_map"], "same_grid": args.same_grid,
+                "deep_map": head["deep_map"], "current_map": head["current_map"], "same_grid": args.same_grid,
                 "executed_ray_steps_per_pass": head["executed_ray_steps_per_pass"],
                 "parallelism": f"rays sharded x{world} ({head['shard']}), fields replicated, no collective",
                 "l2": head["l2"],

@@ -57,7 +57,6 @@ static constexpr int kBlock = kBlockThreads;
 #ifndef MR_MIN_BLOCKS
 #define MR_MIN_BLOCKS 7
 #endif
-// the ray state of the current step in shared memory instead of registers (fast path)
 // experiment knob: the redundant all-NaN test of k0 (see solout below).  Without it ptxas (12.9) spills the
 // pre-step state around the stage loop unless that state is parked in shared memory (MR_FIN_SHADOW): measured
 // on C4, 51.0 ms with the test, 49.7 ms without it and with the shadow.
@@ -67,15 +66,7 @@ static constexpr int kBlock = kBlockThreads;
 #ifndef MR_FIN_SHADOW
 #define MR_FIN_SHADOW 1
 #endif
-#ifndef MR_ROW_POINTER
-#define MR_ROW_POINTER 1
-#endif
-#ifndef MR_Y_SHARED
-#define MR_Y_SHARED 0
-#endif
-#ifndef MR_ACC_SHARED
-#define MR_ACC_SHARED 0
-#endif
+
 // grids whose f32 coordinates are not affine keep the per-cell corner coordinates and basis live: more registers
 #ifndef MR_MIN_BLOCKS_GENERIC
 #define MR_MIN_BLOCKS_GENERIC 5
@@ -136,59 +127,37 @@ trace_kernel(const __grid_constant__ TraceArgs a)
     const double half = dt / 2.0;
     const int32_t nsteps = (int32_t)a.nsteps;      // < 2^31 (mr_num_steps)
 
-    // The state (x, y, kx, ky) of the step being taken.  MR_Y_SHARED: it lives in shared memory (32 bytes per
-    // thread, each thread its own slots, no synchronisation) instead of eight registers that would otherwise be
-    // live through every right-hand side; it is read once per stage and written once per step.
-    constexpr bool kYsh = MR_Y_SHARED && MATH == MR_MATH_FAST;
-    __shared__ double ysh[kYsh ? 4 : 1][kYsh ? kBlock : 1];
-    // MR_ACC_SHARED: the RK4 accumulator k0 + 2 k1 + 2 k2 + k3 likewise (read and written once per stage)
-    constexpr bool kAsh = MR_ACC_SHARED && MATH == MR_MATH_FAST;
-    __shared__ double ash[kAsh ? 4 : 1][kAsh ? kBlock : 1];
-    double yreg[4];
-    auto Y = [&](int c) -> double & { return kYsh ? ysh[c][threadIdx.x] : yreg[c]; };
-    auto load_state = [&](double out[4]) {
-#pragma unroll
-        for (int c = 0; c < 4; ++c) out[c] = Y(c);
-    };
-    // MR_ROW_POINTER: the thread carries a pointer to its element of the last stored row; otherwise only the
-    // (warp-uniform) row number is carried and the address is formed when a row is stored
-    // MR_FIN_SHADOW: the state before the step is parked in shared memory (each thread its own slots) for the one
-    // event that needs it — the first NaN, when the last NaN-free state is written out — instead of being held in
-    // registers, or spilled to local memory by the compiler, through the update
-    constexpr bool kShadow = MR_FIN_SHADOW && MATH == MR_MATH_FAST && !kYsh;
+    double y[4];                           // the state (x, y, kx, ky) of the step being taken
+    // MR_FIN_SHADOW: the state before the step is parked in shared memory (each thread its own slots, no
+    // synchronisation) for the one event that needs it — the first NaN, when the last NaN-free state is written
+    // out — instead of being held in registers, or spilled to local memory by the compiler, through the update
+    constexpr bool kShadow = MR_FIN_SHADOW && MATH == MR_MATH_FAST;
     __shared__ double yprev[kShadow ? 4 : 1][kShadow ? kBlock : 1];
-    char *p = nullptr;                     // this ray's element of the last stored row of the x plane
-    int32_t row = 0;                       // the last stored row
-    auto row_ptr = [&]() -> char * {
-        return MR_ROW_POINTER ? p : (char *)(a.x + ray_index(a)) + (int64_t)row * a.row_bytes;
-    };
+    char *p;                               // this ray's element of the last stored row of the x plane
     bool alive = nsteps > 0;
     bool clean;                            // no NaN seen yet: rows so far all count towards len
     {
         const int64_t i = ray_index(a);
-        const double y0[4] = {a.x0[i], a.y0[i], a.kx0[i], a.ky0[i]};
-#pragma unroll
-        for (int c = 0; c < 4; ++c) Y(c) = y0[c];
-        if (MR_ROW_POINTER) p = (char *)(a.x + i);
-        clean = !any_nan4(y0);
+        y[0] = a.x0[i]; y[1] = a.y0[i]; y[2] = a.kx0[i]; y[3] = a.ky0[i];
+        p = (char *)(a.x + i);
+        clean = !any_nan4(y);
         if (!clean) {                      // no NaN-free row at all
             if (a.len) store_count(a, a.len, 0);
             if (a.fin) { const double nanrow[4] = {qnan(), qnan(), qnan(), qnan()}; store_fin(a, nanrow); }
         }
-        if (store) store_row(a, row_ptr(), y0);
+        if (store) store_row(a, p, y);
     }
 
     int32_t until_store = a.stride;        // counts down to the next stored row
     for (int32_t s = 1; s <= nsteps; ++s) {
         if (!__any_sync(0xffffffffu, alive)) break;
         if (alive) {
-            double k[1][4], accreg[4];
-            auto ACC = [&](int c) -> double & { return kAsh ? ash[c][threadIdx.x] : accreg[c]; };
+            double k[1][4], acc[4];
 #if MR_K0_TEST
             bool k0_nan;
 #endif
 #pragma unroll
-            for (int c = 0; c < 4; ++c) { k[0][c] = 0.0; ACC(c) = -0.0; }    // -0 + k0 == k0 for every k0
+            for (int c = 0; c < 4; ++c) { k[0][c] = 0.0; acc[c] = -0.0; }    // -0 + k0 == k0 for every k0
 #pragma unroll kStageUnroll
             for (int st = 0; st < 4; ++st) {
                 const double as = (st == 0) ? 0.0 : (st == 3 ? dt : half);
@@ -196,44 +165,35 @@ trace_kernel(const __grid_constant__ TraceArgs a)
                 double yt[1][4];
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
-                    const double yc = Y(c);
-                    const double adv = (MATH == MR_MATH_STRICT) ? __dadd_rn(yc, __dmul_rn(k[0][c], as)) : fma(k[0][c], as, yc);
+                    const double adv = (MATH == MR_MATH_STRICT) ? __dadd_rn(y[c], __dmul_rn(k[0][c], as)) : fma(k[0][c], as, y[c]);
                     // stage 0 evaluates f(y): k is 0 there, and y + 0*0 == y (a -0 component would become
                     // +0, which the strict path must not allow)
-                    yt[0][c] = (MATH == MR_MATH_STRICT && st == 0) ? yc : adv;
+                    yt[0][c] = (MATH == MR_MATH_STRICT && st == 0) ? y[c] : adv;
                 }
                 rhs<BK, CK, MATH, UNI, 1, DMAP, SG, CMAP>(a.b, a.c, yt, k);
 #if MR_K0_TEST
                 if (st == 0) k0_nan = all_nan4(k[0]);
 #endif
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const double ac = ACC(c);
-                    ACC(c) = (MATH == MR_MATH_STRICT) ? __dadd_rn(ac, __dmul_rn(k[0][c], ws)) : fma(k[0][c], ws, ac);
-                }
+                for (int c = 0; c < 4; ++c)
+                    acc[c] = (MATH == MR_MATH_STRICT) ? __dadd_rn(acc[c], __dmul_rn(k[0][c], ws)) : fma(k[0][c], ws, acc[c]);
             }
             double yn[4];
             if (kShadow && a.fin) {
 #pragma unroll
-                for (int c = 0; c < 4; ++c) yprev[c][threadIdx.x] = Y(c);
+                for (int c = 0; c < 4; ++c) yprev[c][threadIdx.x] = y[c];
             }
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const double yc = Y(c), ac = ACC(c);
-                yn[c] = (MATH == MR_MATH_STRICT) ? __dadd_rn(yc, __dmul_rn(ac, sixth)) : fma(ac, sixth, yc);
-            }
+            for (int c = 0; c < 4; ++c)
+                yn[c] = (MATH == MR_MATH_STRICT) ? __dadd_rn(y[c], __dmul_rn(acc[c], sixth)) : fma(acc[c], sixth, y[c]);
             const bool n0 = isnan(yn[0]), n1 = isnan(yn[1]), n2 = isnan(yn[2]), n3 = isnan(yn[3]);
             if (clean && (n0 || n1 || n2 || n3)) {
                 clean = false;
                 if (a.len) store_count(a, a.len, s);
                 if (a.fin) {                          // the row before this one is the last NaN-free state
                     double yo[4];
-                    if (kShadow) {
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) yo[c] = yprev[c][threadIdx.x];
-                    } else {
-                        load_state(yo);
-                    }
+                    for (int c = 0; c < 4; ++c) yo[c] = kShadow ? yprev[c][threadIdx.x] : y[c];
                     store_fin(a, yo);
                 }
             }
@@ -248,34 +208,22 @@ trace_kernel(const __grid_constant__ TraceArgs a)
                 if (a.rows) store_count(a, a.rows, s + 1);
             }
 #pragma unroll
-            for (int c = 0; c < 4; ++c) Y(c) = yn[c];
+            for (int c = 0; c < 4; ++c) y[c] = yn[c];
         }
         if (--until_store == 0) {
             until_store = a.stride;
-            if (MR_ROW_POINTER) p += a.row_bytes; else ++row;
-            if (store) {
-                double yo[4];
-                load_state(yo);
-                store_row(a, row_ptr(), yo);
-            }
+            p += a.row_bytes;
+            if (store) store_row(a, p, y);
         }
     }
     // whole warp stopped early: the rows it never reached are NaN (how many is read off the row pointer,
     // so that nothing but the pointer is carried through the loop for it)
     if (store) {
         const double nanrow[4] = {qnan(), qnan(), qnan(), qnan()};
-        if (MR_ROW_POINTER) {
-            char *const last = (char *)(a.x + ray_index(a)) + (int64_t)(nsteps / a.stride) * a.row_bytes;
-            while (p != last) {
-                p += a.row_bytes;
-                store_row(a, p, nanrow);
-            }
-        } else {
-            const int32_t last = nsteps / a.stride;
-            while (row != last) {
-                ++row;
-                store_row(a, row_ptr(), nanrow);
-            }
+        char *const last = (char *)(a.x + ray_index(a)) + (int64_t)(nsteps / a.stride) * a.row_bytes;
+        while (p != last) {
+            p += a.row_bytes;
+            store_row(a, p, nanrow);
         }
     }
     // a ray still integrating when the loop ends ran all nsteps (nsteps == 0: the initial row only);
@@ -285,11 +233,7 @@ trace_kernel(const __grid_constant__ TraceArgs a)
     }
     if (clean) {
         if (a.len) store_count(a, a.len, nsteps + 1);
-        if (a.fin) {
-            double yo[4];
-            load_state(yo);
-            store_fin(a, yo);
-        }
+        if (a.fin) store_fin(a, y);
     }
 }
 

@@ -234,15 +234,19 @@ def run_reference(args):
     if rank != 0:
         return
     wl = make_workload(args.workload, max(args.gpus, 1), args.rays_per_gpu)
-    cb = cpu_leg(wl, seconds_per_step=10.0, steps=max(args.steps, 1), warmup=min(args.warmup, 1))
+    # the whole run is bounded to about a minute and a half of CPU passes whatever --steps is: ~10 s per pass for a
+    # few steps, shorter passes (never below 2 s: 16 threads need that to amortise their start) for many
+    steps = max(args.steps, 1)
+    cb = cpu_leg(wl, seconds_per_step=min(10.0, max(2.0, 75.0 / steps)), steps=steps, warmup=min(args.warmup, 1))
     line = {
         "impl": "reference",
         "metric": METRIC, "value": cb["value"], "unit": UNIT,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl.name, "description": wl.description, "rays": wl.n_rays, "rk4_steps": wl.n_steps,
-                   "grid": [wl.bathymetry.x.size, wl.bathymetry.y.size], "stride": wl.stride},
+        "config": {"workload": wl.name, "description": wl.description, "rays": wl.n_rays,
+                   "rays_per_gpu": wl.n_rays // max(args.gpus, 1), "rk4_steps": wl.n_steps,
+                   "grid": [int(wl.bathymetry.x.size), int(wl.bathymetry.y.size)], "stride": wl.stride, "output": wl.output},
         "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "warmup_passes_run": min(args.warmup, 1),   # a CPU pass takes ~10 s: at most one is spent untimed

@@ -90,7 +90,7 @@ if __name__ == "__main__":
     ap.add_argument("--child", default=None)
     ap.add_argument("--notraj", action="store_true")
     ap.add_argument("--nx", type=int, default=2048)
-    ap.add_argument("--flags", type=int, default=0, help="mr_trace_opts.flags (0 = library default, 1 = MR_OPT_DEEP_MAP, 2 = MR_OPT_NO_DEEP_MAP)")
+    ap.add_argument("--flags", type=int, default=0, help="mr_trace_opts.flags: 0 = library default, 1 / 2 = depth-floor map on / off, 4 = same-grid shortcut, 8 / 16 = uniform-current map on / off")
     ap.add_argument("--order", default="start", choices=["start", "dir", "tile", "tile32"],
                     help="C4 only: order of the same rays (start-point-major as benchmarked, direction-major, or tiled)")
     ap.add_argument("libs", nargs="*")

@@ -78,8 +78,8 @@ def parse():
     ap.add_argument("--math", default="fast", choices=["fast", "strict"])
     ap.add_argument("--deep-map", default="auto", choices=["auto", "on", "off"],
                     help="depth-floor map of the fast path (mr_trace_opts.flags): the library's own choice, forced on, forced off")
-    ap.add_argument("--same-grid", default="off", choices=["off", "on"],
-                    help="same-grid shortcut of the fast path (MR_OPT_SAME_GRID, opt-in)")
+    ap.add_argument("--same-grid", default="auto", choices=["auto", "off", "on"],
+                    help="same-grid shortcut of the fast path (auto: the library's rule — where no map is in use; MR_OPT_[NO_]SAME_GRID)")
     ap.add_argument("--shard", default="auto", choices=["auto", "block", "interleave"],
                     help="how the ensemble is shared out over the ranks: one contiguous block each, or tiles dealt round-robin "
                          "(auto: interleave for C5, whose period bands differ in work; block otherwise)")
@@ -380,8 +380,7 @@ def main():
     sm_count = torch.cuda.get_device_properties(local).multi_processor_count
     flush_buf = [None]
     flags = {"auto": 0, "on": _abi.MR_OPT_DEEP_MAP, "off": _abi.MR_OPT_NO_DEEP_MAP}[args.deep_map]
-    if args.same_grid == "on":
-        flags |= _abi.MR_OPT_SAME_GRID
+    flags |= {"auto": 0, "on": _abi.MR_OPT_SAME_GRID, "off": _abi.MR_OPT_NO_SAME_GRID}[args.same_grid]
 
     def run_workload(name, steps, warmup, rays_per_gpu, sampler=None):
         """Times `steps` device-resident passes of workload `name` on this rank's share, after `warmup` untimed ones.
@@ -400,17 +399,17 @@ def main():
         d_len = torch.empty(n, dtype=torch.int32, device=dev)
         d_fin = torch.empty((4, n), dtype=torch.float64, device=dev)
         opts = _abi.TraceOpts(wl.stride, math_mode, 0, flags)
-        # what the library does with those flags on this grid (include/mantaray_b200.h): the map exists on affine
-        # gridded bathymetry, and the default uses it when a quarter of its blocks are deep for a 10 s wave
-        deep_map_used, deep_share = False, None
+        # what the library does with those flags on this grid (mr_trace_plan; include/mantaray_b200.h): the depth-floor
+        # map when a quarter of the bathymetry's blocks are deep for a 10 s wave, the uniform-current map when half of
+        # the current's blocks are uniform, the same-grid shortcut where the grids coincide and neither map is in use
+        plan = fields.plan(math_mode, flags)
+        deep_map_used, cur_map_used = bool(plan & _abi.MR_PLAN_DEEP_MAP), bool(plan & _abi.MR_PLAN_CURRENT_MAP)
+        same_grid_used = bool(plan & _abi.MR_PLAN_SAME_GRID)
+        deep_share, cur_share = None, None
         if args.math == "fast" and isinstance(wl.bathymetry, CartesianNetcdf3):
-            _, deep_share, affine = _capi.depth_floor_map(wl.bathymetry)
-            deep_map_used = bool(affine) and args.deep_map != "off" and (args.deep_map == "on" or deep_share >= 0.25)
-        # likewise the uniform-current map: on affine current grids whose blocks are at least half uniform
-        cur_map_used, cur_share = False, None
-        if args.math == "fast" and args.same_grid == "off" and isinstance(wl.current, CartesianCurrent):
-            _, cur_share, c_affine = _capi.uniform_current_map(wl.current)
-            cur_map_used = bool(c_affine) and cur_share >= 0.5
+            _, deep_share, _ = _capi.depth_floor_map(wl.bathymetry)
+        if args.math == "fast" and isinstance(wl.current, CartesianCurrent):
+            _, cur_share, _ = _capi.uniform_current_map(wl.current)
         launches = C.c_int32(0)
         p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
 
@@ -470,11 +469,11 @@ def main():
         ach_tf = alg_flop / (kernel_ms * 1e-3) / 1e12
         ach_gbs = alg_bytes / (kernel_ms * 1e-3) / 1e9
         variant = [args.math] + (["depth-floor map"] if deep_map_used else []) + (["uniform-current map"] if cur_map_used else []) + \
-                  (["same-grid"] if args.same_grid == "on" else [])
+                  (["same-grid"] if same_grid_used else [])
         kname = "mr::trace_kernel<GRID,GRID,%s>" % ",".join(variant)
         hw, traffic = None, None
         cap = hw_counters.get(wl.name)
-        if cap and args.math == "fast" and bool(cap.get("deep_map")) == deep_map_used and args.same_grid == "off":
+        if cap and args.math == "fast" and bool(cap.get("deep_map")) == deep_map_used and bool(cap.get("same_grid")) == same_grid_used:
             # the hardware's own count of the same kernel, from the committed ncu capture (a smaller launch of the same
             # shape; per-cycle rates do not depend on the launch size)
             fpc = cap["dadd_per_cycle"] + cap["dmul_per_cycle"] + 2.0 * cap["dfma_per_cycle"]
@@ -537,6 +536,7 @@ def main():
             "per_rank_ms": per_rank_ms, "imbalance_max_over_mean": max(per_rank_ms) / (sum(per_rank_ms) / len(per_rank_ms)),
             "deep_map": {"flag": args.deep_map, "used": deep_map_used, "deep_share_of_blocks": deep_share},
             "current_map": {"used": cur_map_used, "uniform_share_of_blocks": cur_share},
+            "same_grid": {"flag": args.same_grid, "used": same_grid_used},
             "l2": ("each pass writes %.1f GB per GPU, far more than the 126 MB L2: no flush needed" % (out_bytes / 1e9)) if not need_flush
                   else "256 MB buffer written before every timed pass (outside the timed interval)",
             "roofline": roofline, "roofline_hbm": roofline_hbm, "parity": parity, "gpu_launches": int(allsum(float(n_launch))),
@@ -641,7 +641,7 @@ def main():
                 "workload": wl.name, "description": wl.description, "rays": wl.n_rays, "rays_per_gpu": n,
                 "rk4_steps": wl.n_steps, "grid": head["grid"],
                 "stride": wl.stride, "output": wl.output, "math": args.math,
-                "deep_map": head["deep_map"], "current_map": head["current_map"], "same_grid": args.same_grid,
+                "deep_map": head["deep_map"], "current_map": head["current_map"], "same_grid": head["same_grid"],
                 "executed_ray_steps_per_pass": head["executed_ray_steps_per_pass"],
                 "parallelism": f"rays sharded x{world} ({head['shard']}), fields replicated, no collective",
                 "l2": head["l2"],

@@ -132,15 +132,18 @@ typedef struct mr_trace_opts {
  *   MR_OPT_NO_DEEP_MAP : never use it (wins over MR_OPT_DEEP_MAP)                                     */
 #define MR_OPT_DEEP_MAP    1
 #define MR_OPT_NO_DEEP_MAP 2
-/* Same-grid shortcut (opt-in).  When the current is given on the bathymetry's own grid (same shape, same
- * coordinates) MR_MATH_FAST can derive the current's cell from the bathymetry's f32 fractional index wherever that
- * index is further from a grid line than the two indices of the reference (f32 for the bathymetry, f64 for the
- * current) can disagree, and evaluate both lookups separately elsewhere: the same cells, hence the same looked-up
- * values, with one index instead of two.  It pays when the rays of a warp cross grid lines together
- * (ensembles of parallel rays: C3 -6 %, C5 -3 % kernel time) and costs when they do not (C4 +2 %, C2 +4 %), so the
- * library does not choose it by itself.  Ignored where the grids differ.
- *   MR_OPT_SAME_GRID : use the shortcut where the two grids coincide                                   */
+/* Same-grid shortcut.  When the current is given on the bathymetry's own grid (same shape, same coordinates)
+ * MR_MATH_FAST can derive the current's cell from the bathymetry's f32 fractional index wherever that index is
+ * further from a grid line than the two indices of the reference (f32 for the bathymetry, f64 for the current) can
+ * disagree, and evaluate both lookups separately elsewhere: the same cells, hence the same looked-up values, with
+ * one index instead of two.  By default the library uses it where the grids coincide and NEITHER map
+ * (depth-floor, uniform-current) is in use: measured there it is never slower (C4, C2 without maps: +0.3 %) and up to
+ * 8 % faster (C3 without maps -8 %, C5 -3 %); beside a map it costs (C4 with the depth-floor map +10 %), because the
+ * maps already skip the work it would share.  Ignored where the grids differ.
+ *   MR_OPT_SAME_GRID    : use the shortcut wherever the two grids coincide, maps or not
+ *   MR_OPT_NO_SAME_GRID : never use it (wins)                                                          */
 #define MR_OPT_SAME_GRID 4
+#define MR_OPT_NO_SAME_GRID 32
 /* Uniform-current map.  The API always takes a current file, so "no current" is a grid of zeros; step currents are
  * piecewise constant.  Where a block of 8 x 8 cells of an affine current grid holds one u and one v, the reference's
  * bilinear returns exactly that value and its finite differences are exactly 0, so MR_MATH_FAST reads 8 bytes of a
@@ -187,6 +190,15 @@ uint32_t mr_fields_device_mask(const mr_fields *f);
  * number of devices in the handle (entries beyond `cap` are not written), or
  * MR_ERR_BAD_ARG. */
 int  mr_fields_last_split(mr_fields *f, int64_t *rays_per_device, int32_t cap);
+
+/* Which specialisations of the kernel a trace with these options runs on this handle (opts NULL = defaults): a
+ * mask of MR_PLAN_* bits, or a negative MR_ERR_*.  The choice never changes rows / len and keeps every value within
+ * the tolerances stated with the MR_OPT_* flags; this is for reports and tests. */
+#define MR_PLAN_AFFINE      1   /* coordinates exactly affine in f32: index and corner arithmetic from launch constants */
+#define MR_PLAN_DEEP_MAP    2   /* depth-floor map    */
+#define MR_PLAN_SAME_GRID   4   /* same-grid shortcut */
+#define MR_PLAN_CURRENT_MAP 8   /* uniform-current map */
+int  mr_trace_plan(const mr_fields *f, const mr_trace_opts *opts);
 
 /* The host-buffer entry points (mr_trace_many, mr_trace_many_env, mr_single_ray)
  * keep their device work buffers in the handle so that the next call does not

@@ -59,7 +59,8 @@ pub struct mr_trace_opts {
 
 pub const MR_OPT_DEEP_MAP: i32 = 1;
 pub const MR_OPT_NO_DEEP_MAP: i32 = 2;
-pub const MR_OPT_SAME_GRID: i32 = 4; // opt-in: one fractional index for both fields on a shared grid
+pub const MR_OPT_SAME_GRID: i32 = 4; // one fractional index for both fields on a shared grid, also beside a map
+pub const MR_OPT_NO_SAME_GRID: i32 = 32; // never (the default uses it where the grids coincide and no map is in use)
 pub const MR_OPT_CURRENT_MAP: i32 = 8;
 pub const MR_OPT_NO_CURRENT_MAP: i32 = 16;
 
@@ -77,6 +78,8 @@ extern "C" {
     pub fn mr_fields_free(f: *mut mr_fields);
     /// rays each device of the handle took from the slab queue in the last host-buffer call; returns the device count
     pub fn mr_fields_last_split(f: *mut mr_fields, rays_per_device: *mut i64, cap: i32) -> i32;
+    /// MR_PLAN_* bits (1 affine, 2 depth-floor map, 4 same-grid shortcut, 8 uniform-current map) of a trace with `opts`
+    pub fn mr_trace_plan(f: *const mr_fields, opts: *const mr_trace_opts) -> c_int;
     pub fn mr_num_rows(t0: f64, t_end: f64, dt: f64, stride: i32) -> i64;
     pub fn mr_trace_many(f: *mut mr_fields, n: i64,
                          x0: *const f64, y0: *const f64, kx0: *const f64, ky0: *const f64,

@@ -9,7 +9,8 @@ library, calling into it does (and fails loudly when it is missing).
 """
 
 from ._abi import (MR_MATH_FAST, MR_MATH_STRICT, MR_OPT_CURRENT_MAP, MR_OPT_DEEP_MAP, MR_OPT_NO_CURRENT_MAP,
-                   MR_OPT_NO_DEEP_MAP, MR_OPT_SAME_GRID)
+                   MR_OPT_NO_DEEP_MAP, MR_OPT_NO_SAME_GRID, MR_OPT_SAME_GRID, MR_PLAN_AFFINE, MR_PLAN_CURRENT_MAP,
+                   MR_PLAN_DEEP_MAP, MR_PLAN_SAME_GRID)
 from ._capi import (Fields, ManyRays, MantarayError, RayState, SingleRay, TraceResult, depth_floor_map, sample_fields, uniform_current_map,
                     trace_many)
 from ._mantaray import cache_info, clear_cache
@@ -22,5 +23,5 @@ __all__ = [
     "ManyRays", "SingleRay", "RayState", "Fields", "TraceResult", "trace_many", "sample_fields", "depth_floor_map", "uniform_current_map",
     "MantarayError",
     "ConstantDepth", "ConstantSlope", "CartesianNetcdf3", "ArrayDepth", "ConstantCurrent", "CartesianCurrent",
-    "MR_MATH_FAST", "MR_MATH_STRICT", "MR_OPT_DEEP_MAP", "MR_OPT_NO_DEEP_MAP", "MR_OPT_SAME_GRID", "MR_OPT_CURRENT_MAP", "MR_OPT_NO_CURRENT_MAP",
+    "MR_MATH_FAST", "MR_MATH_STRICT", "MR_OPT_DEEP_MAP", "MR_OPT_NO_DEEP_MAP", "MR_OPT_SAME_GRID", "MR_OPT_NO_SAME_GRID", "MR_PLAN_AFFINE", "MR_PLAN_DEEP_MAP", "MR_PLAN_SAME_GRID", "MR_PLAN_CURRENT_MAP", "MR_OPT_CURRENT_MAP", "MR_OPT_NO_CURRENT_MAP",
 ]

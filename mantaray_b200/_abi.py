@@ -73,8 +73,10 @@ class CurrentDesc(C.Structure):
 MR_OPT_DEEP_MAP = 1
 MR_OPT_NO_DEEP_MAP = 2
 MR_OPT_SAME_GRID = 4
+MR_OPT_NO_SAME_GRID = 32
 MR_OPT_CURRENT_MAP = 8
 MR_OPT_NO_CURRENT_MAP = 16
+MR_PLAN_AFFINE, MR_PLAN_DEEP_MAP, MR_PLAN_SAME_GRID, MR_PLAN_CURRENT_MAP = 1, 2, 4, 8
 
 
 class TraceOpts(C.Structure):
@@ -157,6 +159,7 @@ SIGNATURES = {
     "mr_nc3_read_f32": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64]),
     "mr_nc3_read_f64": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64]),
     "mr_fields_last_split": (C.c_int, [C.c_void_p, c_int64_p, C.c_int32]),
+    "mr_trace_plan": (C.c_int, [C.c_void_p, C.POINTER(TraceOpts)]),
     "mr_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
     "mr_host_free": (None, [C.c_void_p]),
     "mr_uniform_current_map": (C.c_int, [C.POINTER(CurrentDesc), C.c_void_p, C.c_size_t, c_int32_p, c_int32_p,

@@ -198,6 +198,15 @@ class Fields:
             _check(n)
         return [int(out[i]) for i in range(n)]
 
+    def plan(self, math: int = 0, flags: int = 0) -> int:
+        """Which kernel specialisations a trace with these options runs on this handle: ``MR_PLAN_*`` bits
+        (``mr_trace_plan``)."""
+        opts = _abi.TraceOpts(1, math, 0, flags)
+        p = int(self._lib.mr_trace_plan(self.handle, C.byref(opts)))
+        if p < 0:
+            _check(p)
+        return p
+
     def trim(self) -> None:
         """Give the cached device work buffers of the host-buffer path back (``mr_fields_trim``)."""
         if self._h:

@@ -509,6 +509,17 @@ static int want_current_map(const DeviceFields &d, const mr_trace_opts &o)
     return (o.flags & MR_OPT_CURRENT_MAP) != 0 || d.cuni_frac >= kCurrentMapAutoShare;
 }
 
+// The same-grid shortcut: on request wherever the grids coincide; by itself only where neither map is in use (beside
+// a map it costs more than it saves, see include/mantaray_b200.h).
+static int want_same_grid(const DeviceFields &d, const mr_trace_opts &o)
+{
+    if ((o.flags & MR_OPT_NO_SAME_GRID) || !d.b.same_grid) return 0;
+    if (o.flags & MR_OPT_SAME_GRID) return 1;
+    const bool dmap = want_deep_map(d, o) && d.b.dmap != nullptr;
+    const bool cmap = want_current_map(d, o) && d.c.cmap != nullptr;
+    return !dmap && !cmap;
+}
+
 static int enqueue_trace(const DeviceFields &d, cudaStream_t stream, int64_t n,
                          const double *x0, const double *y0, const double *kx0, const double *ky0,
                          double dt, int64_t nsteps, const mr_trace_opts &o,
@@ -522,7 +533,7 @@ static int enqueue_trace(const DeviceFields &d, cudaStream_t stream, int64_t n,
     a.x = x; a.y = y; a.kx = kx; a.ky = ky; a.ld = ld;
     a.rows = rows; a.len = len; a.fin = fin;
     a.deep_map = want_deep_map(d, o);
-    a.same_grid = (o.flags & MR_OPT_SAME_GRID) != 0;
+    a.same_grid = want_same_grid(d, o);
     a.current_map = want_current_map(d, o);
     cudaError_t e;
     if (o.math == MR_MATH_STRICT) e = launch_trace_strict(a, stream);
@@ -731,7 +742,7 @@ static int trace_slabs_on_device(DeviceFields &d, const HostJob &j, SlabQueue &q
                 a.ld = chunk;
                 a.rows = B.rows; a.len = B.len; a.fin = B.fin;
                 a.deep_map = want_deep_map(d, j.o);
-                a.same_grid = (j.o.flags & MR_OPT_SAME_GRID) != 0;
+                a.same_grid = want_same_grid(d, j.o);
                 a.current_map = want_current_map(d, j.o);
                 // fin is [4][n] with n = m for the kernel (it uses a.n as the pitch)
                 cudaError_t e = j.o.math == MR_MATH_STRICT ? launch_trace_strict(a, s_comp) : launch_trace_fast(a, s_comp);
@@ -940,6 +951,22 @@ int mr_fields_last_split(mr_fields *f, int64_t *rays_per_device, int32_t cap)
     const int n = (int)f->devs.size();
     for (int g = 0; g < n && g < cap; ++g) rays_per_device[g] = f->devs[(size_t)g].last_taken;
     return n;
+}
+
+int mr_trace_plan(const mr_fields *f, const mr_trace_opts *opts)
+{
+    MR_API_BEGIN
+    if (!f || f->devs.empty()) return fail(MR_ERR_BAD_ARG, "mr_trace_plan: NULL handle");
+    mr_trace_opts o = opts ? *opts : mr_trace_opts{1, MR_MATH_FAST, 0, 0};
+    if (o.math != MR_MATH_FAST && o.math != MR_MATH_STRICT) return fail(MR_ERR_BAD_ARG, "mr_trace_opts.math must be MR_MATH_FAST or MR_MATH_STRICT");
+    const DeviceFields &d = f->devs[0];          // every device holds the same fields
+    TraceArgs a{};
+    a.b = d.b; a.c = d.c;
+    a.deep_map = want_deep_map(d, o); a.same_grid = want_same_grid(d, o); a.current_map = want_current_map(d, o);
+    const TracePlan p = plan_of(a, o.math == MR_MATH_FAST);
+    return (p.uni ? MR_PLAN_AFFINE : 0) | (p.dmap ? MR_PLAN_DEEP_MAP : 0) | (p.sg ? MR_PLAN_SAME_GRID : 0) |
+           (p.cmap ? MR_PLAN_CURRENT_MAP : 0);
+    MR_API_END("mr_trace_plan")
 }
 
 void mr_fields_trim(mr_fields *f)

@@ -49,6 +49,25 @@ struct TraceArgs {
 
 static constexpr int kBlock = kBlockThreads;
 
+// Which specialisations of the kernel a launch with these arguments runs (launch_trace_math dispatches on it,
+// mr_trace_plan reports it).
+struct TracePlan {
+    bool uni;    // affine-coordinate fast path: every gridded field qualifies
+    bool dmap;   // depth-floor map: the affine fast path on a gridded bathymetry that has one
+    bool sg;     // same-grid shortcut: both fields gridded, affine, and on one grid (BathyDev::same_grid, set at upload)
+    bool cmap;   // uniform-current map: the affine fast path on a gridded current that has one (not with the shortcut)
+};
+inline TracePlan plan_of(const TraceArgs &a, bool fast)
+{
+    TracePlan p;
+    p.uni = fast && (a.b.kind != MR_BATHY_GRID || a.b.uniform) && (a.c.kind != MR_CURRENT_GRID || a.c.uniform) &&
+            (a.b.kind == MR_BATHY_GRID || a.c.kind == MR_CURRENT_GRID);
+    p.dmap = p.uni && a.deep_map && a.b.kind == MR_BATHY_GRID && a.b.dmap != nullptr;
+    p.sg = p.uni && a.same_grid && a.b.kind == MR_BATHY_GRID && a.c.kind == MR_CURRENT_GRID && a.b.same_grid;
+    p.cmap = p.uni && !p.sg && a.current_map && a.c.kind == MR_CURRENT_GRID && a.c.cmap != nullptr;
+    return p;
+}
+
 // build-time tuning knobs (see profiles/): unroll factor of the RK4 stage loop and the
 // resident-blocks-per-SM target of the fast kernel
 #ifndef MR_STAGE_UNROLL
@@ -247,18 +266,10 @@ static cudaError_t launch_trace_math(const TraceArgs &args, cudaStream_t stream)
     a.off_y = (const char *)a.y - (const char *)a.x; a.off_kx = (const char *)a.kx - (const char *)a.x;
     a.off_ky = (const char *)a.ky - (const char *)a.x; a.row_bytes = a.ld * (int64_t)sizeof(double);
     a.sixth = a.dt / 6.0;
-    // the fast path's affine-coordinate specialisation needs every gridded field to qualify
-    const bool uni = MATH == MR_MATH_FAST &&
-                     (a.b.kind != MR_BATHY_GRID || a.b.uniform) && (a.c.kind != MR_CURRENT_GRID || a.c.uniform) &&
-                     (a.b.kind == MR_BATHY_GRID || a.c.kind == MR_CURRENT_GRID);
+    const TracePlan plan = plan_of(a, MATH == MR_MATH_FAST);
+    const bool uni = plan.uni, dmap = plan.dmap, sg = plan.sg, cmap = plan.cmap;
     const unsigned grid = (unsigned)((a.n + (int64_t)kBlock - 1) / (int64_t)kBlock);
     constexpr bool kFast = MATH == MR_MATH_FAST;
-    // the depth-floor map needs the affine fast path on a gridded bathymetry that has one
-    const bool dmap = uni && a.deep_map && a.b.kind == MR_BATHY_GRID && a.b.dmap != nullptr;
-    // the same-grid shortcut needs both fields gridded, affine, and on one grid (BathyDev::same_grid, set at upload)
-    const bool sg = uni && a.same_grid && a.b.kind == MR_BATHY_GRID && a.c.kind == MR_CURRENT_GRID && a.b.same_grid;
-    // the uniform-current map needs the affine fast path on a gridded current that has one (not with the shortcut)
-    const bool cmap = uni && !sg && a.current_map && a.c.kind == MR_CURRENT_GRID && a.c.cmap != nullptr;
 #define MR_LAUNCH(BKV, CKV, UNIV)                                                                              \
     do {                                                                                                       \
         constexpr bool kGG = kFast && UNIV && BKV == MR_BATHY_GRID && CKV == MR_CURRENT_GRID;                  \

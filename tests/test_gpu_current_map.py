@@ -13,7 +13,8 @@ import pytest
 from conftest import assert_parity
 from mantaray_b200 import MR_MATH_FAST, CartesianCurrent, CartesianNetcdf3, Fields, trace_many
 from mantaray_b200 import workloads as W
-from mantaray_b200._abi import MR_OPT_CURRENT_MAP, MR_OPT_DEEP_MAP, MR_OPT_NO_CURRENT_MAP, MR_OPT_NO_DEEP_MAP
+from mantaray_b200._abi import (MR_OPT_CURRENT_MAP, MR_OPT_DEEP_MAP, MR_OPT_NO_CURRENT_MAP, MR_OPT_NO_DEEP_MAP,
+                                MR_OPT_NO_SAME_GRID)
 
 pytestmark = pytest.mark.gpu
 
@@ -27,8 +28,11 @@ def assert_identical(a, b, what):
 def run_all(bathy, cur, rays, t_end, dt, stride=1):
     out = {}
     with Fields(bathy, cur, devices=[0]) as f:
-        for name, flags in (("off", MR_OPT_NO_CURRENT_MAP | MR_OPT_NO_DEEP_MAP), ("on", MR_OPT_CURRENT_MAP | MR_OPT_NO_DEEP_MAP),
-                            ("off+depth map", MR_OPT_NO_CURRENT_MAP | MR_OPT_DEEP_MAP), ("on+depth map", MR_OPT_CURRENT_MAP | MR_OPT_DEEP_MAP),
+        # (without either map the library would take the same-grid shortcut by itself where the grids coincide: the
+        # map is compared with the plain lookups)
+        nsg = MR_OPT_NO_SAME_GRID
+        for name, flags in (("off", MR_OPT_NO_CURRENT_MAP | MR_OPT_NO_DEEP_MAP | nsg), ("on", MR_OPT_CURRENT_MAP | MR_OPT_NO_DEEP_MAP | nsg),
+                            ("off+depth map", MR_OPT_NO_CURRENT_MAP | MR_OPT_DEEP_MAP | nsg), ("on+depth map", MR_OPT_CURRENT_MAP | MR_OPT_DEEP_MAP | nsg),
                             ("default", 0)):
             out[name] = trace_many(f, *rays, 0.0, t_end, dt, stride=stride, math=MR_MATH_FAST, final_state=True, flags=flags)
     return out

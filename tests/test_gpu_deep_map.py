@@ -17,14 +17,15 @@ import pytest
 from conftest import assert_parity
 from mantaray_b200 import MR_MATH_FAST, CartesianCurrent, CartesianNetcdf3, ConstantCurrent, Fields, trace_many
 from mantaray_b200 import workloads as W
-from mantaray_b200._abi import MR_OPT_DEEP_MAP, MR_OPT_NO_DEEP_MAP
+from mantaray_b200._abi import MR_OPT_DEEP_MAP, MR_OPT_NO_DEEP_MAP, MR_OPT_NO_SAME_GRID, MR_PLAN_DEEP_MAP, MR_PLAN_SAME_GRID
 from test_gpu_fuzz import make_case
 
 pytestmark = pytest.mark.gpu
 
 
 def both(f, rays, t_end, dt, **kw):
-    plain = trace_many(f, *rays, 0.0, t_end, dt, math=MR_MATH_FAST, final_state=True, flags=MR_OPT_NO_DEEP_MAP, **kw)
+    # (plain = the separate lookups: without a map the library would take the same-grid shortcut by itself)
+    plain = trace_many(f, *rays, 0.0, t_end, dt, math=MR_MATH_FAST, final_state=True, flags=MR_OPT_NO_DEEP_MAP | MR_OPT_NO_SAME_GRID, **kw)
     mapped = trace_many(f, *rays, 0.0, t_end, dt, math=MR_MATH_FAST, final_state=True, flags=MR_OPT_DEEP_MAP, **kw)
     return plain, mapped
 
@@ -56,7 +57,7 @@ def assert_same(mapped, plain, what, exact=False):
 def same_grid_pair(f, rays, t_end, dt, **kw):
     """(separate lookups, same-grid shortcut), both without the map"""
     from mantaray_b200._abi import MR_OPT_SAME_GRID
-    sep = trace_many(f, *rays, 0.0, t_end, dt, math=MR_MATH_FAST, final_state=True, flags=MR_OPT_NO_DEEP_MAP, **kw)
+    sep = trace_many(f, *rays, 0.0, t_end, dt, math=MR_MATH_FAST, final_state=True, flags=MR_OPT_NO_DEEP_MAP | MR_OPT_NO_SAME_GRID, **kw)
     sg = trace_many(f, *rays, 0.0, t_end, dt, math=MR_MATH_FAST, final_state=True,
                     flags=MR_OPT_NO_DEEP_MAP | MR_OPT_SAME_GRID, **kw)
     return sep, sg
@@ -128,21 +129,30 @@ def test_blocks_with_dry_and_non_finite_nodes_fall_back_to_the_lookup(oracle, gp
 
 
 def test_default_follows_the_deep_share_of_the_grid(gpu):
-    """flags = 0: the map is used on C4's deep basin (share >= 1/4) and not on C5's 400 m shelf; either way the
-    rows are those of both forced variants, and MR_OPT_NO_DEEP_MAP wins over MR_OPT_DEEP_MAP."""
+    """flags = 0: the map is used on C4's deep basin (share >= 1/4) and not on C5's 400 m shelf — there, with no map
+    in use and the current on the bathymetry's grid, the same-grid shortcut is; the library says so (mr_trace_plan)
+    and the results are those of the forced variant, bit for bit.  MR_OPT_NO_DEEP_MAP wins over MR_OPT_DEEP_MAP."""
     from mantaray_b200 import depth_floor_map
+    from mantaray_b200._abi import MR_OPT_SAME_GRID
     for wl, deep in ((W.c4_agulhas(16, 16, 300, nx=256), True), (W.c5_nazare(4, 4, 16, 600, nx=512), False)):
         _, share, affine = depth_floor_map(wl.bathymetry)
         assert affine and (share >= 0.25) == deep
         rays = wl.all_rays()
         with Fields(wl.bathymetry, wl.current, devices=[0]) as f:
+            plan = f.plan()
+            assert bool(plan & MR_PLAN_DEEP_MAP) == deep and bool(plan & MR_PLAN_SAME_GRID) == (not deep)
+            assert f.plan(flags=MR_OPT_NO_SAME_GRID | MR_OPT_NO_DEEP_MAP) & (MR_PLAN_DEEP_MAP | MR_PLAN_SAME_GRID) == 0
+            assert f.plan(math=1) == 0                                   # MR_MATH_STRICT has no specialisations
             plain, mapped = both(f, rays, wl.duration, wl.dt, stride=wl.stride)
+            shortcut = trace_many(f, *rays, 0.0, wl.duration, wl.dt, final_state=True, stride=wl.stride,
+                                  flags=MR_OPT_NO_DEEP_MAP | MR_OPT_SAME_GRID)
             auto = trace_many(f, *rays, 0.0, wl.duration, wl.dt, final_state=True, stride=wl.stride)
             off = trace_many(f, *rays, 0.0, wl.duration, wl.dt, final_state=True, stride=wl.stride,
-                             flags=MR_OPT_DEEP_MAP | MR_OPT_NO_DEEP_MAP)
-        assert_same(auto, mapped if deep else plain, "default flags", exact=True)
+                             flags=MR_OPT_DEEP_MAP | MR_OPT_NO_DEEP_MAP | MR_OPT_NO_SAME_GRID)
+        assert_same(auto, mapped if deep else shortcut, "default flags", exact=True)
         assert_same(off, plain, "both flags", exact=True)
         assert_same(mapped, plain, "forced")
+        assert_same(shortcut, plain, "same-grid shortcut")
 
 
 def test_steep_cells_at_large_indices(oracle, gpu):

@@ -1,4 +1,4 @@
-"""The same-grid shortcut (include/mantaray_b200.h MR_OPT_SAME_GRID, opt-in).
+"""The same-grid shortcut (include/mantaray_b200.h MR_OPT_SAME_GRID / MR_OPT_NO_SAME_GRID).
 
 When the current is given on the bathymetry's own grid the fast path derives the current's cell from the
 bathymetry's f32 fractional index (cartesian_netcdf3.rs:289) instead of forming the f64 index of
@@ -16,7 +16,7 @@ import pytest
 from conftest import assert_parity
 from mantaray_b200 import MR_MATH_FAST, CartesianCurrent, CartesianNetcdf3, Fields, trace_many
 from mantaray_b200 import workloads as W
-from mantaray_b200._abi import MR_OPT_DEEP_MAP, MR_OPT_NO_DEEP_MAP, MR_OPT_SAME_GRID
+from mantaray_b200._abi import MR_OPT_DEEP_MAP, MR_OPT_NO_DEEP_MAP, MR_OPT_NO_SAME_GRID, MR_OPT_SAME_GRID
 
 pytestmark = pytest.mark.gpu
 
@@ -99,7 +99,7 @@ def test_same_grid_shortcut_names_the_same_cells_near_grid_lines(oracle, gpu, nx
     t_end = 12 * dt
     ref = oracle.trace_many(bathy, cur, *rays, 0.0, t_end, dt)
     with Fields(bathy, cur, devices=[0]) as f:
-        sep = trace_many(f, *rays, 0.0, t_end, dt, math=MR_MATH_FAST, final_state=True, flags=MR_OPT_NO_DEEP_MAP)
+        sep = trace_many(f, *rays, 0.0, t_end, dt, math=MR_MATH_FAST, final_state=True, flags=MR_OPT_NO_DEEP_MAP | MR_OPT_NO_SAME_GRID)
         sg = trace_many(f, *rays, 0.0, t_end, dt, math=MR_MATH_FAST, final_state=True, flags=MR_OPT_NO_DEEP_MAP | MR_OPT_SAME_GRID)
         sg_map = trace_many(f, *rays, 0.0, t_end, dt, math=MR_MATH_FAST, final_state=True, flags=MR_OPT_DEEP_MAP | MR_OPT_SAME_GRID)
         auto = trace_many(f, *rays, 0.0, t_end, dt, math=MR_MATH_FAST, final_state=True, flags=MR_OPT_SAME_GRID)
@@ -121,7 +121,7 @@ def test_named_workloads_take_the_shortcut_and_agree(oracle, gpu, name, make):
     rays = wl.all_rays()
     ref = oracle.trace_many(wl.bathymetry, wl.current, *rays, 0.0, wl.duration, wl.dt, stride=wl.stride)
     with Fields(wl.bathymetry, wl.current, devices=[0]) as f:
-        sep = trace_many(f, *rays, 0.0, wl.duration, wl.dt, stride=wl.stride, final_state=True, flags=MR_OPT_NO_DEEP_MAP)
+        sep = trace_many(f, *rays, 0.0, wl.duration, wl.dt, stride=wl.stride, final_state=True, flags=MR_OPT_NO_DEEP_MAP | MR_OPT_NO_SAME_GRID)
         sg = trace_many(f, *rays, 0.0, wl.duration, wl.dt, stride=wl.stride, final_state=True, flags=MR_OPT_NO_DEEP_MAP | MR_OPT_SAME_GRID)
         auto = trace_many(f, *rays, 0.0, wl.duration, wl.dt, stride=wl.stride, final_state=True, flags=MR_OPT_SAME_GRID)
     assert_same_cells(sg, sep, f"{name}: same-grid vs separate")
@@ -141,7 +141,7 @@ def test_grids_that_only_look_alike_do_not_take_the_shortcut(oracle, gpu):
         ref = oracle.trace_many(bathy, c2, *rays, 0.0, t_end, dt)
         with Fields(bathy, c2, devices=[0]) as f:
             a = trace_many(f, *rays, 0.0, t_end, dt, final_state=True, flags=MR_OPT_NO_DEEP_MAP | MR_OPT_SAME_GRID)
-            b = trace_many(f, *rays, 0.0, t_end, dt, final_state=True, flags=MR_OPT_NO_DEEP_MAP)
+            b = trace_many(f, *rays, 0.0, t_end, dt, final_state=True, flags=MR_OPT_NO_DEEP_MAP | MR_OPT_NO_SAME_GRID)
         for nm in ("rows", "len", "x", "y", "kx", "ky"):
             np.testing.assert_array_equal(getattr(a, nm), getattr(b, nm), err_msg=nm)
         assert_parity(a, ref, what="look-alike grids")

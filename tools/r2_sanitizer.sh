@@ -1,4 +1,4 @@
-# compute-sanitizer memcheck over the fast / strict / depth-floor-map / same-grid / environment kernels on a subset
+# compute-sanitizer memcheck over the fast / strict / depth-floor-map / same-grid / uniform-current-map / environment kernels on a subset
 # of the parity suites (small cases: the tool slows kernels ~50x)
 #   gpurun --timeout 900 -- 'bash tools/r2_sanitizer.sh r2s'
 set -x
@@ -17,6 +17,7 @@ MR_FUZZ_SEEDS=8 run fuzz tests/test_gpu_fuzz.py
 MR_FUZZ_SEEDS=6 run deepmap_fuzz tests/test_gpu_deep_map.py -k "fuzz or steep"
 run deepmap tests/test_gpu_deep_map.py -k "dry or default or C4"
 run samegrid tests/test_gpu_same_grid.py -k "64-48 or look_alike or C5"
+run currentmap tests/test_gpu_current_map.py -k "patchwork or C2 or C5"
 run env tests/test_gpu_env.py -k "not full"
 run parity tests/test_gpu_parity.py -k "special or infinite or empty or analytic or shoreline"
 run api tests/test_gpu_api.py -k "grid_lines or non_affine or negative or pitch or multiple"

@@ -655,7 +655,7 @@ static int trace_slabs_on_device(DeviceFields &d, const HostJob &j, SlabQueue &q
         const double env_row = (j.env.depth ? 4.0 : 0.0) + (j.env.u ? 8.0 : 0.0) + (j.env.v ? 8.0 : 0.0);
         const double per_ray = 32.0 + (want_traj ? (32.0 + env_row) * (double)j.rows_cap : 0.0) + 8.0 + 32.0;
         const double budget = 0.80 * (double)(free_b + w.held());      // what this handle already holds is ours to reuse
-        const int64_t wave = 148 * 4 * kBlock;              // rays that fill the machine once
+        const int64_t wave = 148 * 512;                     // slab sizes are rounded to this many rays (four 128-ray groups per SM)
         if (j.o.chunk_rays > 0) {
             chunk = std::min<int64_t>(n, j.o.chunk_rays);
         } else {
@@ -668,12 +668,12 @@ static int trace_slabs_on_device(DeviceFields &d, const HostJob &j, SlabQueue &q
             }
             if (shared_queue) {
                 // several devices on one queue: about sixteen slabs per device, so that the last slab a device
-                // takes is a small share of its work — but a slab fills the machine (7 blocks on each of 148 SMs)
+                // takes is a small share of its work — but a slab fills the machine (28 warps on each of 148 SMs)
                 // unless the batch is too small to give every device that much
-                const int64_t G = q.devices, full = 148 * 7 * kBlock;
+                const int64_t G = q.devices, full = kMachineRays;
                 const int64_t per_dev = (n + G - 1) / G, target = (n + G * 16 - 1) / (G * 16);
                 int64_t want = std::max(target, std::min(full, per_dev));
-                want = (want + kBlock - 1) / kBlock * kBlock;
+                want = (want + 127) / 128 * 128;
                 chunk = std::min(chunk, want);
             }
             chunk = std::max<int64_t>(std::min(chunk, n), 1);

@@ -137,7 +137,15 @@ struct CurrentDev {
 };
 
 static constexpr double kG = 9.8;            // src/wave_ray_path.rs:23
-static constexpr int kBlockThreads = 128;    // threads per block of the trace kernel
+// Threads per block of the trace kernel: ONE warp.  A block's slot on the SM is free again as soon as its last ray
+// has stopped, without waiting for sibling warps; measured against 64 and 128 threads per block (the same 28 warps per
+// SM): C4 49.1 / 49.5 / 49.7 ms, the other shapes unchanged (profiles/r2/kbench_r2k14_block_size.txt).
+#ifndef MR_BLOCK_THREADS
+#define MR_BLOCK_THREADS 32
+#endif
+static constexpr int kBlockThreads = MR_BLOCK_THREADS;
+static constexpr int kWarpsPerSM = 28;                          // resident warps per SM the fast kernels are built for (72 registers)
+static constexpr int kMachineRays = 148 * kWarpsPerSM * 32;     // rays that fill a B200 once
 
 // Taylor coefficients 1/13! .. 1/2! of expm1 (see exp_expm1_neg).  In constant memory so
 // that each DFMA reads its coefficient as a c[bank][offset] operand instead of the

@@ -69,12 +69,12 @@ inline TracePlan plan_of(const TraceArgs &a, bool fast)
 }
 
 // build-time tuning knobs (see profiles/): unroll factor of the RK4 stage loop and the
-// resident-blocks-per-SM target of the fast kernel
+// resident-blocks-per-SM target of the fast kernel (28 warps per SM: 72 registers)
 #ifndef MR_STAGE_UNROLL
 #define MR_STAGE_UNROLL 1
 #endif
 #ifndef MR_MIN_BLOCKS
-#define MR_MIN_BLOCKS 7
+#define MR_MIN_BLOCKS (kWarpsPerSM * 32 / kBlockThreads)
 #endif
 // experiment knob: the redundant all-NaN test of k0 (see solout below).  Without it ptxas (12.9) spills the
 // pre-step state around the stage loop unless that state is parked in shared memory (MR_FIN_SHADOW): measured
@@ -88,11 +88,11 @@ inline TracePlan plan_of(const TraceArgs &a, bool fast)
 
 // grids whose f32 coordinates are not affine keep the per-cell corner coordinates and basis live: more registers
 #ifndef MR_MIN_BLOCKS_GENERIC
-#define MR_MIN_BLOCKS_GENERIC 5
+#define MR_MIN_BLOCKS_GENERIC (20 * 32 / kBlockThreads)
 #endif
 // the depth-floor-map variant carries a little more state per thread
 #ifndef MR_MIN_BLOCKS_DMAP
-#define MR_MIN_BLOCKS_DMAP 7
+#define MR_MIN_BLOCKS_DMAP (kWarpsPerSM * 32 / kBlockThreads)
 #endif
 static constexpr int kStageUnroll = MR_STAGE_UNROLL;
 // (Two rays per thread — interleaved RHS phases, 16-byte row stores — was measured at 2.0e10 ray-steps/s

@@ -78,6 +78,8 @@ def test_descriptor_validation_messages():
     assert lib.mr_fields_create(C.byref(b), C.byref(c), 1, C.byref(h)) == _abi.MR_ERR_BAD_ARG
     assert lib.mr_fields_create(None, C.byref(c), 1, C.byref(h)) == _abi.MR_ERR_BAD_ARG
     assert lib.mr_trace_many(None, 1, None, None, None, None, 0.0, 1.0, 1.0, None, *([None] * 8)) == _abi.MR_ERR_BAD_ARG
+    assert lib.mr_trace_plan(None, None) == _abi.MR_ERR_BAD_ARG
+    assert b"NULL handle" in lib.mr_last_error()
 
 
 def _build_cpp_example(tmp_path):

@@ -45,6 +45,9 @@ struct TraceArgs {
     // filled by launch_trace_math: the trajectory planes as byte offsets from the x plane, the row pitch in bytes
     int64_t off_y, off_kx, off_ky, row_bytes;
     double sixth;              // dt / 6 (read from here by the depth-floor-map variant, which is short of registers)
+    // the stage offsets {0, dt/2, dt/2, dt} and weights {1, 2, 2, 1} of RK4: the looped stages index them with the
+    // stage number (one constant-bank load each) instead of deriving them with compares and branches
+    double stage_a[4], stage_w[4];
 };
 
 static constexpr int kBlock = kBlockThreads;
@@ -72,6 +75,9 @@ inline TracePlan plan_of(const TraceArgs &a, bool fast)
 // resident-blocks-per-SM target of the fast kernel (28 warps per SM: 72 registers)
 #ifndef MR_STAGE_UNROLL
 #define MR_STAGE_UNROLL 1
+#endif
+#ifndef MR_STAGE_TABLE
+#define MR_STAGE_TABLE 1
 #endif
 #ifndef MR_MIN_BLOCKS
 #define MR_MIN_BLOCKS (kWarpsPerSM * 32 / kBlockThreads)
@@ -179,8 +185,12 @@ trace_kernel(const __grid_constant__ TraceArgs a)
             for (int c = 0; c < 4; ++c) { k[0][c] = 0.0; acc[c] = -0.0; }    // -0 + k0 == k0 for every k0
 #pragma unroll kStageUnroll
             for (int st = 0; st < 4; ++st) {
-                const double as = (st == 0) ? 0.0 : (st == 3 ? dt : half);
-                const double ws = (st == 1 || st == 2) ? 2.0 : 1.0;
+                // the uniform-current-map kernels read the stage constants from the parameter bank (TraceArgs::stage_a):
+                // C2 46.7 against 47.4 ms, C3 40.5 against 41.3; the others derive them (C4 the same either way, the
+                // same-grid kernel 1 % slower with the table: ptxas spills 14 bytes there)
+                constexpr bool kTable = MR_STAGE_TABLE && MATH == MR_MATH_FAST && CMAP;
+                const double as = kTable ? a.stage_a[st] : ((st == 0) ? 0.0 : (st == 3 ? dt : half));
+                const double ws = kTable ? a.stage_w[st] : ((st == 1 || st == 2) ? 2.0 : 1.0);
                 double yt[1][4];
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
@@ -266,6 +276,8 @@ static cudaError_t launch_trace_math(const TraceArgs &args, cudaStream_t stream)
     a.off_y = (const char *)a.y - (const char *)a.x; a.off_kx = (const char *)a.kx - (const char *)a.x;
     a.off_ky = (const char *)a.ky - (const char *)a.x; a.row_bytes = a.ld * (int64_t)sizeof(double);
     a.sixth = a.dt / 6.0;
+    a.stage_a[0] = 0.0; a.stage_a[1] = a.stage_a[2] = a.dt / 2.0; a.stage_a[3] = a.dt;
+    a.stage_w[0] = a.stage_w[3] = 1.0; a.stage_w[1] = a.stage_w[2] = 2.0;
     const TracePlan plan = plan_of(a, MATH == MR_MATH_FAST);
     const bool uni = plan.uni, dmap = plan.dmap, sg = plan.sg, cmap = plan.cmap;
     const unsigned grid = (unsigned)((a.n + (int64_t)kBlock - 1) / (int64_t)kBlock);

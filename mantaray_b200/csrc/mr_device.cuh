@@ -747,7 +747,7 @@ struct FastRay {
             } else {
                 ok = ix >= 0.0f && ix <= b.nxm1f && iy >= 0.0f && iy <= b.nym1f;  // :291
             }
-            brec = b.cell + 2u * (unsigned)((b.nx - 1) * by1 + bx1);
+            brec = b.cell + 2ull * (unsigned)((b.nx - 1) * by1 + bx1);
             if (kDmap)
                 asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(hsq)
                              : "l"(b.dmap + (unsigned)((by1 >> kDeepShift) * b.dmap_nbx + (bx1 >> kDeepShift))));
@@ -799,8 +799,8 @@ struct FastRay {
             // the lanes outside uniform blocks fetch their record when they get to the bilinear (current_part):
             // one more exposed round trip for them, sixteen registers fewer held by everybody
         } else if (CK == MR_CURRENT_GRID) {
-            ldg_f4_f4(c.cell + 4u * ccell, U, V);
-            ldg_d2_d2((const double2 *)(c.cell + 4u * ccell + 2), gu, gv);
+            ldg_f4_f4(c.cell + 4ull * ccell, U, V);
+            ldg_d2_d2((const double2 *)(c.cell + 4ull * ccell + 2), gu, gv);
             if (!UNI) {
                 cxa = __ldg(c.xf + cx1); cxb = __ldg(c.xf + cx1 + 1);
                 cya = __ldg(c.yf + cy1); cyb = __ldg(c.yf + cy1 + 1);
@@ -889,8 +889,8 @@ struct FastRay {
             return;
         }
         if (kCmap) {
-            ldg_f4_f4(c.cell + 4u * ccell, U, V);
-            ldg_d2_d2((const double2 *)(c.cell + 4u * ccell + 2), gu, gv);
+            ldg_f4_f4(c.cell + 4ull * ccell, U, V);
+            ldg_d2_d2((const double2 *)(c.cell + 4ull * ccell + 2), gu, gv);
         }
         if (CK == MR_CURRENT_GRID) {
             float X, Y;
@@ -995,7 +995,7 @@ struct FastRay {
             if (MR_DMAP_LATE_LOAD) {
                 // the lanes that need the depth after all: cell, record address and the record itself, now
                 if (!kSame) bathy_cell_again(b);
-                brec = b.cell + 2u * (unsigned)((b.nx - 1) * by1 + bx1);
+                brec = b.cell + 2ull * (unsigned)((b.nx - 1) * by1 + bx1);
                 ldg_f4_d2(brec, Z, gh);
             }
             bathy_part(b, p, h32, dhdx, dhdy, kShare ? &g : nullptr);

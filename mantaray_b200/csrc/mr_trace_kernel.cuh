@@ -77,7 +77,7 @@ inline TracePlan plan_of(const TraceArgs &a, bool fast)
 #define MR_STAGE_UNROLL 1
 #endif
 #ifndef MR_STAGE_TABLE
-#define MR_STAGE_TABLE 1
+#define MR_STAGE_TABLE 3          // bit 0: uniform-current-map kernels, bit 1: same-grid kernel (see the stage loop)
 #endif
 #ifndef MR_MIN_BLOCKS
 #define MR_MIN_BLOCKS (kWarpsPerSM * 32 / kBlockThreads)
@@ -95,6 +95,11 @@ inline TracePlan plan_of(const TraceArgs &a, bool fast)
 // grids whose f32 coordinates are not affine keep the per-cell corner coordinates and basis live: more registers
 #ifndef MR_MIN_BLOCKS_GENERIC
 #define MR_MIN_BLOCKS_GENERIC (20 * 32 / kBlockThreads)
+#endif
+// the same-grid kernel (no map) at 24 warps per SM: 80 registers, nothing spilled — with the stage table C5 70.2
+// against 71.3 ms at 28 warps without it, C3 with both maps off 52.1 against 53.3 (profiles/r2/kbench_r2k16_same_grid_24_warps.txt)
+#ifndef MR_MIN_BLOCKS_SG
+#define MR_MIN_BLOCKS_SG (24 * 32 / kBlockThreads)
 #endif
 // the depth-floor-map variant carries a little more state per thread
 #ifndef MR_MIN_BLOCKS_DMAP
@@ -143,7 +148,7 @@ __device__ __forceinline__ void store_count(const TraceArgs &a, int32_t *dst, in
 // appears (each at most once per ray, re-deriving the ray index on the spot), so the step loop carries two
 // flags and one row pointer per thread; the step number and the store countdown are warp-uniform.
 template <int BK, int CK, int MATH, bool UNI, bool DMAP, bool SG, bool CMAP>
-__global__ void __launch_bounds__(kBlock, (MATH == MR_MATH_FAST) ? (UNI ? (DMAP ? MR_MIN_BLOCKS_DMAP : MR_MIN_BLOCKS) : MR_MIN_BLOCKS_GENERIC) : 1)
+__global__ void __launch_bounds__(kBlock, (MATH == MR_MATH_FAST) ? (UNI ? (DMAP ? MR_MIN_BLOCKS_DMAP : (SG ? MR_MIN_BLOCKS_SG : MR_MIN_BLOCKS)) : MR_MIN_BLOCKS_GENERIC) : 1)
 trace_kernel(const __grid_constant__ TraceArgs a)
 {
     const bool store = a.x != nullptr;
@@ -185,10 +190,10 @@ trace_kernel(const __grid_constant__ TraceArgs a)
             for (int c = 0; c < 4; ++c) { k[0][c] = 0.0; acc[c] = -0.0; }    // -0 + k0 == k0 for every k0
 #pragma unroll kStageUnroll
             for (int st = 0; st < 4; ++st) {
-                // the uniform-current-map kernels read the stage constants from the parameter bank (TraceArgs::stage_a):
-                // C2 46.7 against 47.4 ms, C3 40.5 against 41.3; the others derive them (C4 the same either way, the
-                // same-grid kernel 1 % slower with the table: ptxas spills 14 bytes there)
-                constexpr bool kTable = MR_STAGE_TABLE && MATH == MR_MATH_FAST && CMAP;
+                // the uniform-current-map kernels and the same-grid kernel read the stage constants from the parameter
+                // bank (TraceArgs::stage_a): C2 46.7 against 47.4 ms, C3 40.5 against 41.3, C5 (with 24 warps per SM) 70.2
+                // against 71.0; the others derive them (C4 the same either way)
+                constexpr bool kTable = MATH == MR_MATH_FAST && (((MR_STAGE_TABLE & 1) && CMAP) || ((MR_STAGE_TABLE & 2) && SG && !DMAP));
                 const double as = kTable ? a.stage_a[st] : ((st == 0) ? 0.0 : (st == 3 ? dt : half));
                 const double ws = kTable ? a.stage_w[st] : ((st == 1 || st == 2) ? 2.0 : 1.0);
                 double yt[1][4];
